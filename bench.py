@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — aggressive inner-loop encoder steps/s (BASELINE.json metric; Yahoo LSTM-VAE, batch 32, seq 200).
+
+One *step* = one iteration of the reference loop text.py:371-391: zero_grad, VAE.loss forward, Σloss,
+backward of mean(loss), clip_grad_norm_(all 13 tensors, 5.0), SGD step on the 6 encoder tensors, next batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+ours:       `value`  fused lagvae_text_inner_step, inputs resident in HBM, CUDA events, max over ranks
+            `e2e`    the drop-in `modules.VAE` API exactly as text.py:373-387 drives it, token ids in PINNED
+                     HOST memory copied H2D every step, Σloss read back D2H every step
+reference:  the CPU port of the reference path (oracle.FastPort: the reference's own torch layer types) on
+            all host cores, each step a bounded sample (B_s of the 32 sentences), rate scaled to full steps.
+N > 1:      one process per GPU (torchrun), batch-sharded data parallel: every rank runs the same step on
+            its own 32-sentence shard, ONE NCCL all-reduce of the flat 53.8 M-float gradient per step, then
+            clip + SGD on the averaged gradient.  Weak scaling: global batch = 32 N.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "vae-lagging-encoder_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "aggressive inner-loop encoder steps/sec (Yahoo LSTM-VAE, batch32 seq200)"
+CFG = dict(V=20001, ni=512, nh=1024, nz=32, B=32, T=200)   # BASELINE.json configs[1], SURVEY §8(d2)
+KL_WEIGHT = 0.1                                           # --kl_start 0.1 (text.py:337-338)
+POOL = 64
+
+
+def flops_step(B, T, V, ni, nh, nz):
+    """F_step = 3 * F_fwd."""
+    Td = T - 1
+    f = 2 * B * (T * ni * 4 * nh + T * nh * 4 * nh + nh * 2 * nz) + \
+        2 * B * (Td * (ni + nz) * 4 * nh + Td * nh * 4 * nh + nz * nh + Td * nh * V)
+    return 3 * f
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: CPU port on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import lagging_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    c = CFG
+    Bs = 4                                            # bounded sample: 4 of the 32 sentences per step
+    torch.manual_seed(0)
+    m = O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).train()
+    xs = [O.make_token_batch(Bs, c["T"], c["V"], seed=1234 + i) for i in range(4)]
+    for i in range(args.warmup):
+        m.inner_step(xs[i % 4], KL_WEIGHT)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m.inner_step(xs[i % 4], KL_WEIGHT)
+    dt = time.perf_counter() - t0
+    rate = args.steps / dt * (Bs / c["B"])            # full 32-sentence steps per second
+    sample = "%d timed steps of %d/%d sentences x T=%d, rate scaled by %d/%d" % (args.steps, Bs, c["B"], c["T"], Bs, c["B"])
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step, B=32 T=200 V=20001 (CPU port, host cores)"},
+            "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_quick():
+    """~10-30 s of CPU work: 2 inner steps on an 8-sentence sample (rank 0, N=1 only)."""
+    import lagging_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    c, Bs = CFG, 8
+    torch.manual_seed(0)
+    m = O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).train()
+    x = O.make_token_batch(Bs, c["T"], c["V"])
+    m.inner_step(x, KL_WEIGHT)
+    t0 = time.perf_counter()
+    n = 2
+    for _ in range(n):
+        m.inner_step(x, KL_WEIGHT)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt * (Bs / c["B"]), "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of %d/%d sentences x T=%d (oracle.FastPort, rate scaled by %d/%d)" % (n, Bs, c["B"], c["T"], Bs, c["B"])}
+
+
+def torch_gpu_port(steps=6):
+    """The same port on THIS GPU through torch's stock cuDNN/cuBLAS path (what the unmodified reference
+    would run on a B200) — informational, the denominator of north_star's >=10x target."""
+    import lagging_oracle as O
+    c = CFG
+    torch.manual_seed(0)
+    m = O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).cuda().train()
+    torch.backends.cudnn.deterministic = True         # text.py:102
+    xs = [O.make_token_batch(c["B"], c["T"], c["V"], seed=99 + i).cuda() for i in range(4)]
+    for i in range(3):
+        m.inner_step(xs[i % 4], KL_WEIGHT)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.inner_step(xs[i % 4], KL_WEIGHT)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    del m
+    torch.cuda.empty_cache()
+    return {"value": steps / dt, "unit": "steps/s", "what": "oracle.FastPort (nn.LSTM/nn.Linear -> cuDNN/cuBLAS fp32) on this GPU",
+            "tf32_matmul": bool(torch.backends.cuda.matmul.allow_tf32), "tf32_cudnn": bool(torch.backends.cudnn.allow_tf32)}
+
+
+def time_vocab_gemm(eng, reps=5):
+    """Dominant tensor kernel timed alone with CUDA events on the launching stream: the vocabulary
+    projection [B*(T-1), nh] x [nh, V] (dec_lstm.py:109), split-bf16 3-pass."""
+    import ctypes as C
+    import lagvae._backend as be
+    c = CFG
+    M, N, K = c["B"] * (c["T"] - 1), c["V"], c["nh"]
+    A = torch.randn(M, K, device="cuda")
+    Bm = torch.randn(N, K, device="cuda") * 0.03
+    ah, al = A.to(torch.bfloat16), (A - A.to(torch.bfloat16).float()).to(torch.bfloat16)
+    bh, bl = Bm.to(torch.bfloat16), (Bm - Bm.to(torch.bfloat16).float()).to(torch.bfloat16)
+    out = torch.empty(M, N, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call = lambda: be.check(be.lib().lagvae_gemm_tc(be.ptr(ah), be.ptr(al), K, 0, be.ptr(bh), be.ptr(bl), K, 0, be.ptr(out), N,
+                                                    M, N, K, 3, 1.0, 0.0, None, None, 0, None, st))
+    for _ in range(2):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return 2.0 * M * N * K, ms
+
+
+def run_ours(args, rank, world, local_rank):
+    import lagvae
+    import lagging_oracle as O
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    c = CFG
+    B, T, V = c["B"], c["T"], c["V"]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # parameters: the reference initialisers (text.py:265-266), identical on every rank
+    p = O.init_text_params(V, c["ni"], c["nh"], c["nz"], seed=0)
+    params = [p[k].to(dev).contiguous() for k in O.ALL_KEYS]
+    eng = lagvae.TextEngine(V, c["ni"], c["nh"], c["nz"], dev)
+    # pool of 64 distinct device-resident batches (per-rank shard: different sentences on each rank)
+    pool = [O.make_token_batch(B, T, V, seed=1234 + 1000 * rank + i).to(dev) for i in range(POOL)]
+    rng = np.random.RandomState(783435)               # text.py:73 seed; picks identical on all ranks
+    picks = [int(rng.randint(0, POOL)) for _ in range(args.warmup + args.steps + 8)]
+    gw = eng.grad_workspace()
+    grads = eng.split_grads(gw)
+    out_loss = torch.empty(B, device=dev)
+    sc = torch.empty(4, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(783435 + rank)
+    seed_ctr = [0]
+
+    def drop():
+        seed_ctr[0] += 1
+        return lagvae.DropoutSpec(2, 0.5, 0.5, None, None, 783435 * 1000003 + seed_ctr[0] * 7919 + rank)
+
+    def step_fused(i):
+        x = pool[picks[i]]
+        eps = torch.empty(B, 1, c["nz"], device=dev).normal_(generator=gen)       # encoder.py:77
+        if world == 1:
+            eng.inner_step(params, x, eps, KL_WEIGHT, drop(), gw, out_loss, sc)   # text.py:373-387 fused
+        else:
+            loss, _, _ = eng.loss_forward(params, x, eps, KL_WEIGHT, drop())
+            gl = torch.full((B,), 1.0 / (B * world), device=dev)                   # mean over the GLOBAL batch
+            eng.loss_backward(params, x, gl, None, None, grads_out=grads)
+            dist.all_reduce(gw)                                                    # ONE all-reduce per inner step
+            eng.clip_sgd(params, grads, 6, 5.0, 1.0, scale_all=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs ----------------
+    for i in range(args.warmup):
+        step_fused(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lagvae.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_fused(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = lagvae.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    clocks = sampler.summary()
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total / 1e3)     # 32-sentence encoder steps per second, all ranks
+
+    # ---------------- e2e: drop-in modules API, host token ids, per-step readback ----------------
+    e2e = None
+    if True:
+        import types
+        import modules
+
+        class Vocab(dict):
+            def __len__(self):
+                return V
+
+            def id2word(self, i):
+                return str(i)
+        a = types.SimpleNamespace(ni=c["ni"], enc_nh=c["nh"], dec_nh=c["nh"], nz=c["nz"], dec_dropout_in=0.5,
+                                  dec_dropout_out=0.5, device=dev)
+        mi_ = lambda t: torch.nn.init.uniform_(t, -0.01, 0.01)
+        ei_ = lambda t: torch.nn.init.uniform_(t, -0.1, 0.1)
+        torch.manual_seed(783435)
+        vae = modules.VAE(modules.LSTMEncoder(a, V, mi_, ei_), modules.LSTMDecoder(a, Vocab(), mi_, ei_), a).to(dev)
+        vae.train()
+        enc_opt = torch.optim.SGD(vae.encoder.parameters(), lr=1.0, momentum=0)
+        dec_opt = torch.optim.SGD(vae.decoder.parameters(), lr=1.0, momentum=0)
+        host_pool = [t.cpu().pin_memory() for t in pool[:16]]
+        xdev = torch.empty(B, T, dtype=torch.int64, device=dev)
+        allp = list(vae.parameters())
+
+        def step_api(i):
+            xdev.copy_(host_pool[picks[i] % 16], non_blocking=True)               # H2D of this step's input
+            enc_opt.zero_grad()
+            dec_opt.zero_grad()
+            loss, loss_rc, loss_kl = vae.loss(xdev, KL_WEIGHT, nsamples=1)        # text.py:379
+            s = loss.sum().item()                                                 # text.py:381 (D2H sync)
+            loss = loss.mean(dim=-1)
+            loss.backward()                                                       # text.py:384
+            if world > 1:
+                for q in allp:
+                    q.grad.div_(world)
+                    dist.all_reduce(q.grad)
+            torch.nn.utils.clip_grad_norm_(allp, 5.0)                             # text.py:385
+            enc_opt.step()                                                        # text.py:387
+            return s
+
+        n_e2e = max(3, min(args.steps, 10))
+        for i in range(2):
+            step_api(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(n_e2e):
+            step_api(2 + i)
+        f1.record()
+        barrier()
+        ems = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n_e2e / (float(ems) / 1e3), "unit": "steps/s", "h2d_bytes_per_step": B * T * 8,
+               "d2h_bytes_per_step": 4, "steps": n_e2e,
+               "api": "modules.VAE.loss -> backward -> clip_grad_norm_ -> SGD.step (text.py:373-387 sequence)"}
+        del vae, enc_opt, dec_opt
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    F = flops_step(B, T, V, c["ni"], c["nh"], c["nz"])
+    gflop, gms = time_vocab_gemm(eng)
+    roof = {"bound": "tensor", "kernel": "k_gemm_tc<K-major,K-major> vocab projection 6368x20001x1024 (split-bf16, 3 MMA passes)",
+            "achieved": gflop / (gms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": gflop / (gms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+            "peak_source": peak_src + " bf16 burst (kernel timed alone); algorithmic FLOPs counted once although 3 bf16 passes are issued",
+            "ms_per_launch": gms,
+            "step_tensor_frac": F / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
+    line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3-split operands, f32 accumulate/state", "data": "synthetic",
+            "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step (text.py:371-391), B=32/GPU T=200 V=20001 ni=512 nh=1024 nz=32, "
+                                   "train-mode dropout 0.5/0.5, kl_weight 0.1, SGD lr 1.0, clip 5.0",
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (509 MB logits + 420 MB gate stashes) exceeds the 126 MB L2; no explicit flush",
+                       "pool": "%d device-resident batches, np.random.seed(783435) picks" % POOL},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "flops_per_step": F, "algorithmic_tflops": F / (ms_per_step * 1e-3) / 1e12}
+    if world == 1 and not args.no_cpu:
+        try:
+            line["torch_gpu_port"] = torch_gpu_port()
+        except Exception as ex:  # informational only
+            line["torch_gpu_port"] = {"error": repr(ex)[:200]}
+        line["cpu_baseline"] = cpu_baseline_quick()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the CPU / torch-GPU side baselines")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

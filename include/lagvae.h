@@ -1,0 +1,183 @@
+/* lagvae.h — C-ABI of liblagvae.so: B200 (sm_100a) kernels for the aggressive-inner-loop hot path
+ * of jxhe/vae-lagging-encoder.
+ *
+ * The reference has NO native/FFI interface (it is pure Python on torch); the
+ * boundary a maintainer binds is therefore the set of torch library calls the reference makes on
+ * the path.  Each entry point below names the reference call site (file:line, relative to the
+ * reference root) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name starts with
+ *    `h_`; `stream` is a cudaStream_t passed as void*.
+ *  - every function returns 0 on success, non-zero on failure (LAGVAE_E_*); the message of the last
+ *    failure on the calling thread is returned by lagvae_last_error().  No exceptions, no
+ *    allocation inside (workspaces are caller-owned; sizes come from *_workspace_bytes queries).
+ *  - there is NO CPU fallback: every compute entry point launches CUDA kernels and fails with
+ *    LAGVAE_E_CUDA when no sm_100 device/context is usable.
+ *  - activations are TIME-MAJOR: row r = t*Bd + bd, where Bd = B*ns decoder rows, bd = b*ns + s
+ *    (sample-major inside a sentence, as dec_lstm.py:87-94).
+ *  - gate order along 4*nh is PyTorch's i,f,g,o.
+ */
+#ifndef LAGVAE_H_
+#define LAGVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAGVAE_OK 0
+#define LAGVAE_E_ARG 1     /* bad argument / unsupported shape */
+#define LAGVAE_E_CUDA 2    /* CUDA runtime / launch failure, or no usable sm_100 device */
+#define LAGVAE_E_WORKSPACE 3
+
+#define LAGVAE_ABI_VERSION 1
+
+int lagvae_abi_version(void);
+const char* lagvae_last_error(void);
+/* 0 if the current device is sm_100 (B200) and kernels can launch; LAGVAE_E_CUDA otherwise. */
+int lagvae_device_check(void);
+/* number of kernels launched by this library on this process since load (bench `gpu_launches`) */
+int64_t lagvae_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Text-path dimensions.  Be = B encoder rows, Bd = B*ns decoder rows, T = token columns of x
+ * (incl. <s>, </s>), Td = T-1 decoder steps.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lagvae_text_dims {
+  int32_t B, T, ns;
+  int32_t V, ni, nh, nz;
+} lagvae_text_dims;
+
+/* The 13 parameter tensors in reference state_dict / vae.parameters() order:
+ * encoder: embed.weight[V,ni] lstm.weight_ih_l0[4nh,ni] lstm.weight_hh_l0[4nh,nh] lstm.bias_ih_l0[4nh]
+ *          lstm.bias_hh_l0[4nh] linear.weight[2nz,nh]
+ * decoder: embed.weight[V,ni] trans_linear.weight[nh,nz] lstm.weight_ih_l0[4nh,ni+nz]
+ *          lstm.weight_hh_l0[4nh,nh] lstm.bias_ih_l0[4nh] lstm.bias_hh_l0[4nh] pred_linear.weight[V,nh]
+ * All fp32, contiguous row-major.  The same struct carries gradient pointers. */
+#define LAGVAE_TEXT_NPARAM 13
+typedef struct lagvae_text_params {
+  float* p[LAGVAE_TEXT_NPARAM];
+} lagvae_text_params;
+
+/* Dropout control (dec_lstm.py:30-31,81,106).  mode 0: identity (eval()).  mode 1: caller-provided
+ * keep masks (uint8, 1 = keep): mask_in [B,Td,ni] (applied before the ns expansion, dec_lstm.py:81
+ * precedes :87), mask_out [Bd,Td,nh].  mode 2: in-kernel counter-based Philox4x32-10 keyed by
+ * (seed, stream id), element index = logical index in the shapes above. */
+typedef struct lagvae_dropout {
+  int32_t mode;
+  float p_in, p_out;
+  const uint8_t* mask_in;
+  const uint8_t* mask_out;
+  uint64_t seed;
+} lagvae_dropout;
+
+/* Opaque per-shape plan: workspace carving + kernel selection. */
+typedef struct lagvae_text_plan lagvae_text_plan;
+
+/* flags for lagvae_text_plan_create */
+#define LAGVAE_PLAN_DEFAULT 0u
+#define LAGVAE_PLAN_FORCE_SIMT 1u   /* use the fp32 SIMT kernels for every contraction */
+#define LAGVAE_PLAN_INFERENCE 2u    /* forward only: no stash for backward */
+
+size_t lagvae_text_workspace_bytes(const lagvae_text_dims* d, uint32_t flags);
+/* `workspace` (device, >= workspace_bytes, 256-B aligned) stays owned by the caller and must
+ * outlive the plan.  h_plan_out receives the handle. */
+int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* workspace,
+                            size_t workspace_bytes, lagvae_text_plan** h_plan_out);
+void lagvae_text_plan_destroy(lagvae_text_plan* plan);
+
+/* VAE.loss forward  — modules/vae.py:79-98 = encoder.py:40-57 (enc_lstm.py:47-64, reparam 59-79,
+ * KL :55) + dec_lstm.py:113-148 (decode 66-111, CrossEntropyLoss :47,143) + vae.py:95,98.
+ *  x      int64 [B,T] row-major (driver-owned, never written)
+ *  eps    fp32 [B,ns,nz]  the N(0,1) draw of encoder.py:77
+ *  out_loss/out_rec/out_kl  fp32 [B];  out_mu/out_logvar fp32 [B,nz]; out_z fp32 [B,ns,nz]
+ *  (any out_* except loss/rec/kl may be NULL). */
+int lagvae_text_loss_forward(lagvae_text_plan* plan, const lagvae_text_params* params,
+                             const int64_t* x, const float* eps, float kl_weight,
+                             const lagvae_dropout* drop, float* out_loss, float* out_rec,
+                             float* out_kl, float* out_mu, float* out_logvar, float* out_z,
+                             void* stream);
+
+/* Backward of the above — the autograd walk of text.py:382-384.  Must follow a
+ * lagvae_text_loss_forward on the same plan (uses its stash).  g_loss/g_rec/g_kl: upstream
+ * gradients of the three outputs, fp32 [B], any may be NULL (= zeros).  `grads` receives the 13
+ * gradients (overwritten, not accumulated); decoder.embed.weight row V-1 gets zeros
+ * (padding_idx=-1, dec_lstm.py:28). */
+int lagvae_text_loss_backward(lagvae_text_plan* plan, const lagvae_text_params* params,
+                              const int64_t* x, const float* g_loss, const float* g_rec,
+                              const float* g_kl, const lagvae_text_params* grads, void* stream);
+
+/* Encoder forward only: enc_lstm.py:47-64 (VAE.encode_stats vae.py:33-40). */
+int lagvae_text_encode_stats(lagvae_text_plan* plan, const lagvae_text_params* params,
+                             const int64_t* x, float* out_mu, float* out_logvar, void* stream);
+
+/* Decoder only: LSTMDecoder.reconstruct_error — dec_lstm.py:113-148 (log_probability :151-161 is its
+ * negation).  z fp32 [B*ns, nz]; out_rec_rows fp32 [B*ns] (row b*ns+s).  Forward only. */
+int lagvae_text_reconstruct_error(lagvae_text_plan* plan, const lagvae_text_params* params,
+                                  const int64_t* x, const float* z, const lagvae_dropout* drop,
+                                  float* out_rec_rows, void* stream);
+
+/* clip_grad_norm_(all params, max_norm) + SGD(momentum 0) on the first `n_update` tensors —
+ * text.py:385 + text.py:387 (optim.SGD text.py:325).  segs: `n_seg` (ptr,count) pairs describing
+ * the gradient tensors; params/grads pair up by index.  out_norm (device fp32[1]) receives the
+ * pre-clip total L2 norm.  scale_all_grads != 0 also multiplies every gradient by the clip
+ * coefficient in place (what clip_grad_norm_ does); 0 skips that write for tensors that are not
+ * updated (their clipped value is dead in the aggressive loop). scratch: device, >= 4 KiB. */
+int lagvae_clip_sgd_step(float* const* h_params, float* const* h_grads, const int64_t* h_counts,
+                         int n_seg, int n_update, float max_norm, float lr, int scale_all_grads,
+                         float* out_norm, void* scratch, void* stream);
+
+/* MI estimate from posterior stats — encoder.py:111-145 (+utils.py:3-16).  mu/logvar [B,nz], eps
+ * [B,nz] (the draw of encoder.py:128).  out_mi: device fp32[1]. */
+int lagvae_mi_estimate(const float* mu, const float* logvar, const float* eps, int B, int nz,
+                       float* out_mi, void* stream);
+
+/* Fused aggressive inner step — one iteration of text.py:371-391 without the host round trips:
+ * zero-grad, loss fwd, Σloss, backward of mean(loss), clip(max_norm) over all 13 grads, SGD on the
+ * 6 encoder tensors.  `grad_ws` is a caller-owned flat fp32 buffer of lagvae_text_param_count()
+ * floats.  out_scalars (device fp32[4]) = {Σloss, Σrec, ΣKL, pre-clip grad norm}. */
+int64_t lagvae_text_param_count(const lagvae_text_dims* d);
+int lagvae_text_inner_step(lagvae_text_plan* plan, const lagvae_text_params* params,
+                           const int64_t* x, const float* eps, float kl_weight,
+                           const lagvae_dropout* drop, float max_norm, float lr, float* grad_ws,
+                           float* out_loss, float* out_scalars, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building blocks (exported for the unit/parity tests; also what the plan calls internally)
+ * ------------------------------------------------------------------------------------------- */
+
+/* C[M,N] (ldc) = alpha * sum_k A(m,k) B(n,k) + beta*C, A(m,k)=A[m*a_rs+k*a_cs], B(n,k)=B[n*b_rs+k*b_cs]
+ * + optional bias_n[N] + optional bias_rows[(m % bias_period), N].  fp32 SIMT reference-grade GEMM
+ * (replaces the cuBLAS sgemm calls behind nn.Linear / the LSTM projections). */
+int lagvae_gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                    int64_t b_cs, float* C, int64_t ldc, int M, int N, int K, float alpha, float beta,
+                    const float* bias_n, const float* bias_rows, int bias_period, void* stream);
+
+/* Tensor-core GEMM on tcgen05 (UMMA, fp32 accumulate in TMEM, TMA operand staging).  Operands are
+ * bf16 split pairs (hi, lo) with x = hi + lo + O(2^-17 |x|); passes = 3 computes
+ * hi*hi + hi*lo + lo*hi (fp32-grade), passes = 1 computes hi*hi only.
+ *  A: a_mn_major == 0 -> [M, lda] row-major (K contiguous), else [K, lda] row-major (M contiguous)
+ *  B: b_mn_major == 0 -> [N, ldb] row-major (K contiguous), else [K, ldb] row-major (N contiguous)
+ *  lda/ldb in elements, multiples of 8; pointers 16-B aligned.  C fp32 [M, ldc]; epilogue as above.
+ *  out_row_map (int32[M] or NULL) scatters output row m to C row out_row_map[m]. */
+int lagvae_gemm_tc(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, int a_mn_major,
+                   const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int b_mn_major, float* C,
+                   int64_t ldc, int M, int N, int K, int passes, float alpha, float beta,
+                   const float* bias_n, const float* bias_rows, int bias_period,
+                   const int32_t* out_row_map, void* stream);
+
+/* fp32 [rows, cols] (ld) -> bf16 hi/lo [rows, ld_out] (zero padded columns cols..ld_out). */
+int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
+                      int64_t ld_out, void* stream);
+
+/* materialise the Philox dropout keep-mask the kernels would use (tests feed it to the oracle) */
+int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAGVAE_H_ */

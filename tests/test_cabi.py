@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports every symbol
+include/lagvae.h declares; the product path refuses to run without a CUDA device (no CPU fallback)."""
+import os
+import re
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "lagvae.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lagvae_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import lagvae._backend as be
+    L = be.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(L, s), "missing export " + s
+        assert s in be.PROTOTYPES, "binding lacks prototype for " + s
+    assert sorted(be.PROTOTYPES) == syms
+    assert L.lagvae_abi_version() == be.ABI_VERSION
+
+
+def test_workspace_query_and_param_count_are_host_only():
+    import ctypes as C
+    import lagvae._backend as be
+    d = be.TextDims(32, 200, 1, 20001, 512, 1024, 32)
+    n = be.lib().lagvae_text_param_count(C.byref(d))
+    assert n == 16605696 + 37185024          # SURVEY §2.1 parameter counts
+    ws = be.lib().lagvae_text_workspace_bytes(C.byref(d), 0)
+    assert 1 << 28 < ws < 1 << 34
+    bad = be.TextDims(0, 200, 1, 20001, 512, 1024, 32)
+    assert be.lib().lagvae_text_workspace_bytes(C.byref(bad), 0) == 0
+
+
+def test_no_cpu_fallback():
+    import lagvae
+    import modules
+    with pytest.raises(lagvae.LagvaeError):
+        lagvae.TextEngine(100, 8, 16, 2, "cpu")
+    a = types.SimpleNamespace(ni=8, enc_nh=16, dec_nh=16, nz=2, dec_dropout_in=0.5, dec_dropout_out=0.5, device="cpu")
+
+    class Vocab(dict):
+        def __len__(self):
+            return 50
+    init = lambda t: torch.nn.init.uniform_(t, -0.01, 0.01)
+    vae = modules.VAE(modules.LSTMEncoder(a, 50, init, init), modules.LSTMDecoder(a, Vocab(), init, init), a)
+    with pytest.raises(lagvae.LagvaeError):
+        vae.loss(torch.zeros(2, 5, dtype=torch.long), 1.0)
+    with pytest.raises(lagvae.LagvaeError):
+        vae.calc_mi_q(torch.zeros(2, 5, dtype=torch.long))
+
+
+def test_state_dict_keys_match_reference():
+    import modules
+    a = types.SimpleNamespace(ni=8, enc_nh=16, dec_nh=16, nz=2, dec_dropout_in=0.5, dec_dropout_out=0.5, device="cpu")
+
+    class Vocab(dict):
+        def __len__(self):
+            return 50
+    init = lambda t: torch.nn.init.uniform_(t, -0.01, 0.01)
+    vae = modules.VAE(modules.LSTMEncoder(a, 50, init, init), modules.LSTMDecoder(a, Vocab(), init, init), a)
+    want = ["encoder.embed.weight", "encoder.lstm.weight_ih_l0", "encoder.lstm.weight_hh_l0",
+            "encoder.lstm.bias_ih_l0", "encoder.lstm.bias_hh_l0", "encoder.linear.weight",
+            "decoder.embed.weight", "decoder.trans_linear.weight", "decoder.lstm.weight_ih_l0",
+            "decoder.lstm.weight_hh_l0", "decoder.lstm.bias_ih_l0", "decoder.lstm.bias_hh_l0",
+            "decoder.pred_linear.weight", "decoder.loss.weight"]
+    assert list(vae.state_dict().keys()) == want
+    assert [n for n, _ in vae.named_parameters()] == want[:-1]
+    assert len(vae.encoder_params()) == 6 and len(vae.decoder_params()) == 7
+    assert vae.decoder.embed.padding_idx == 49
+
+
+def test_philox_host_device_contract():
+    """Philox4x32-10 known-answer (Random123 kat: counter=0,key=0)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c, k = [0, 0, 0, 0], [0, 0]
+    for _ in range(10):
+        hi0, lo0 = (M0 * c[0]) >> 32, (M0 * c[0]) & 0xFFFFFFFF
+        hi1, lo1 = (M1 * c[2]) >> 32, (M1 * c[2]) & 0xFFFFFFFF
+        c = [hi1 ^ c[1] ^ k[0], lo1, hi0 ^ c[3] ^ k[1], lo0]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    assert c == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]

@@ -1,0 +1,168 @@
+"""GPU unit tests of the building-block kernels, called through the C-ABI (ctypes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _be():
+    import lagvae._backend as be
+    return be
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (37, 91, 53), (130, 257, 129), (5, 200, 50), (300, 7, 1000)])
+@pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_f32(M, N, K, at, bt):
+    be = _be()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn((K, M) if at else (M, K), generator=g, device="cuda")
+    B = torch.randn((K, N) if bt else (N, K), generator=g, device="cuda")
+    C0 = torch.randn(M, N + 3, generator=g, device="cuda")
+    Cc = C0.clone()
+    bias = torch.randn(N, generator=g, device="cuda")
+    rows = torch.randn(4, N, generator=g, device="cuda")
+    a_rs, a_cs = (1, M) if at else (K, 1)
+    b_rs, b_cs = (1, N) if bt else (K, 1)
+    be.check(be.lib().lagvae_gemm_f32(be.ptr(A), a_rs, a_cs, be.ptr(B), b_rs, b_cs, be.ptr(Cc), N + 3, M, N, K,
+                                      0.5, 2.0, be.ptr(bias), be.ptr(rows), 4, _st()))
+    Ad = (A.t() if at else A).double()
+    Bd = (B.t() if bt else B).double()
+    ref = 0.5 * Ad @ Bd.t() + 2.0 * C0[:, :N].double() + bias.double() + rows.double()[torch.arange(M, device="cuda") % 4]
+    err = float((Cc[:, :N].double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err
+    assert torch.equal(Cc[:, N:], C0[:, N:])
+
+
+def test_split_bf16():
+    be = _be()
+    x = torch.randn(33, 50, device="cuda") * 3
+    hi = torch.zeros(33, 56, dtype=torch.bfloat16, device="cuda")
+    lo = torch.zeros_like(hi)
+    be.check(be.lib().lagvae_split_bf16(be.ptr(x), 50, 33, 50, be.ptr(hi), be.ptr(lo), 56, _st()))
+    rec = hi.float() + lo.float()
+    assert float((rec[:, :50] - x).abs().max() / x.abs().max()) < 2.0 ** -15
+    assert float(rec[:, 50:].abs().max()) == 0.0
+    h2, l2 = _split(x)
+    assert torch.equal(hi[:, :50], h2) and torch.equal(lo[:, :50], l2)
+
+
+TC_SHAPES = [(128, 128, 64), (256, 384, 192), (200, 130, 100), (129, 257, 72), (1000, 96, 520), (64, 520, 4096),
+             (4096, 64, 160)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+@pytest.mark.parametrize("amn,bmn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_tc(M, N, K, amn, bmn, passes):
+    be = _be()
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 5 * K)
+    pad8 = lambda v: (v + 7) // 8 * 8
+    A = torch.randn(M, K, generator=g, device="cuda")
+    B = torch.randn(N, K, generator=g, device="cuda")
+    Ast = torch.zeros((K, pad8(M)) if amn else (M, pad8(K)), device="cuda")
+    Bst = torch.zeros((K, pad8(N)) if bmn else (N, pad8(K)), device="cuda")
+    if amn:
+        Ast[:, :M] = A.t()
+    else:
+        Ast[:, :K] = A
+    if bmn:
+        Bst[:, :N] = B.t()
+    else:
+        Bst[:, :K] = B
+    ah, al = _split(Ast)
+    bh, bl = _split(Bst)
+    Cc = torch.full((M, N + 1), 7.0, device="cuda")
+    bias = torch.randn(N, generator=g, device="cuda")
+    be.check(be.lib().lagvae_gemm_tc(be.ptr(ah), be.ptr(al), Ast.shape[1], amn, be.ptr(bh), be.ptr(bl), Bst.shape[1],
+                                     bmn, be.ptr(Cc), N + 1, M, N, K, passes, 1.0, 0.0, be.ptr(bias), None, 0, None,
+                                     _st()))
+    torch.cuda.synchronize()
+    if passes == 3:
+        ref = A.double() @ B.double().t() + bias.double()
+        tol = 3e-5
+    else:
+        ref = A.to(torch.bfloat16).double() @ B.to(torch.bfloat16).double().t() + bias.double()
+        tol = 1e-5
+    scale = float((A.double().abs() @ B.double().abs().t()).max())
+    err = float((Cc[:, :N].double() - ref).abs().max()) / scale
+    assert err < tol, "rel err %.3e" % err
+    assert float((Cc[:, N] - 7.0).abs().max()) == 0.0
+
+
+def test_gemm_tc_beta_rows_and_map():
+    be = _be()
+    M, N, K = 260, 140, 200
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    ah, al = _split(A)
+    bh, bl = _split(B)
+    C0 = torch.randn(M, N, device="cuda")
+    Cc = C0.clone()
+    rows = torch.randn(13, N, device="cuda")
+    perm = torch.randperm(M, device="cuda").to(torch.int32)
+    be.check(be.lib().lagvae_gemm_tc(be.ptr(ah), be.ptr(al), K, 0, be.ptr(bh), be.ptr(bl), K, 0, be.ptr(Cc), N, M, N, K, 3,
+                                     0.25, 1.0, None, be.ptr(rows), 13, be.ptr(perm), _st()))
+    prod = 0.25 * A.double() @ B.double().t() + rows.double()[torch.arange(M, device="cuda") % 13]
+    ref = C0.double().clone()
+    ref[perm.long()] += prod
+    assert float((Cc.double() - ref).abs().max() / ref.abs().max()) < 3e-5
+
+
+def test_dropout_mask_statistics_and_determinism():
+    be = _be()
+    n = 1 << 20
+    m1 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m2 = torch.empty_like(m1)
+    m3 = torch.empty_like(m1)
+    be.check(be.lib().lagvae_dropout_mask(1234, 1, n, 0.5, be.ptr(m1), _st()))
+    be.check(be.lib().lagvae_dropout_mask(1234, 1, n, 0.5, be.ptr(m2), _st()))
+    be.check(be.lib().lagvae_dropout_mask(1234, 2, n, 0.5, be.ptr(m3), _st()))
+    assert torch.equal(m1, m2)
+    assert abs(float(m1.float().mean()) - 0.5) < 3e-3
+    assert abs(float((m1 == m3).float().mean()) - 0.5) < 3e-3
+
+
+def test_mi_estimate_matches_oracle():
+    import lagging_oracle as O
+    be = _be()
+    for B, nz in [(32, 32), (5, 3), (64, 1), (100, 8)]:
+        mu, lv, eps = torch.randn(B, nz), 0.3 * torch.randn(B, nz), torch.randn(B, 1, nz)
+        want = O.calc_mi_from_stats(mu.double(), lv.double(), eps.double())
+        out = torch.empty(1, device="cuda")
+        be.check(be.lib().lagvae_mi_estimate(be.ptr(mu.cuda()), be.ptr(lv.cuda()), be.ptr(eps.cuda()), B, nz, be.ptr(out), _st()))
+        assert abs(float(out) - want) <= 1e-4 * max(1.0, abs(want)), (float(out), want)
+
+
+def test_clip_sgd_matches_torch():
+    be = _be()
+    for scale in (0.1, 30.0):      # below / above the clip threshold
+        ps = [torch.randn(n, device="cuda") for n in (1000, 77, 5000, 3)]
+        gs = [scale * torch.randn_like(p) for p in ps]
+        ref_p = [p.clone().requires_grad_(True) for p in ps]
+        for rp, g in zip(ref_p, gs):
+            rp.grad = g.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref_p, 5.0)
+        torch.optim.SGD(ref_p[:2], lr=1.0).step()
+        n = len(ps)
+        P = (C.c_void_p * n)(*[p.data_ptr() for p in ps])
+        G = (C.c_void_p * n)(*[g.data_ptr() for g in gs])
+        cnt = (C.c_int64 * n)(*[g.numel() for g in gs])
+        norm = torch.empty(1, device="cuda")
+        scratch = torch.empty(4096, dtype=torch.uint8, device="cuda")
+        be.check(be.lib().lagvae_clip_sgd_step(P, G, cnt, n, 2, 5.0, 1.0, 1, be.ptr(norm), be.ptr(scratch), _st()))
+        assert abs(float(norm) - float(norm_ref)) < 1e-5 * float(norm_ref)
+        for p, rp, g in zip(ps, ref_p, gs):
+            assert float((p - rp.detach()).abs().max()) < 1e-6 * max(1.0, float(rp.abs().max()))
+            assert float((g - rp.grad).abs().max()) < 1e-6 * max(1.0, float(rp.grad.abs().max()))

@@ -1,0 +1,343 @@
+// Split-bf16 tensor-core GEMM on tcgen05 (sm_100a).
+//
+//   C[M,N] = alpha * Σ_k A(m,k) B(n,k) (+ beta C) (+ bias),   A = A_hi + A_lo,  B = B_hi + B_lo (bf16)
+//   passes = 3:  A_hi·B_hi + A_hi·B_lo + A_lo·B_hi   (relative error ~2^-16 per product: fp32-grade,
+//                needed for the 1e-4 parity bar, SURVEY §7 hard part 2)
+//   passes = 1:  A_hi·B_hi
+//
+// Persistent warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, SWIZZLE_128B, 3-stage mbarrier ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128x128x16, fp32 accumulators in TMEM,
+//                               double-buffered: 2 x 128 columns)
+//   warps 2-5   epilogue       (tcgen05.ld 32x32b.x32 -> registers -> bias/alpha/beta -> global)
+// Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the latter is
+// what every weight-gradient GEMM (dW = dYᵀ·X) needs, so no transposes are ever materialised.
+// Replaces the cuBLAS sgemm calls under nn.Linear / nn.LSTM projections of the reference
+// (dec_lstm.py:109, enc_lstm.py:60, dec_lstm.py:104 and their autograd backward, text.py:384).
+#include "lagvae_common.cuh"
+#include "sm100_ptx.cuh"
+
+#include <mutex>
+
+namespace lagvae {
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return LAGVAE_E_CUDA;
+  }
+  LV_CHECK_ARG(((uintptr_t)base & 15) == 0 && (ld % 8) == 0, "tensor map: base must be 16-B aligned, ld %% 8 == 0");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return LAGVAE_E_CUDA;
+  }
+  return LAGVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device kernel
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;            // 16 KiB per operand part
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi A_lo B_hi B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+struct GemmArgs {
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  int passes;
+  float alpha, beta;
+  const float* bias_n;
+  const float* bias_rows;
+  int bias_period;
+  const int32_t* row_map;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+          const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[3] empty[3] tfull[2] tempty[2] ; then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blks = (g.M + BM - 1) / BM, n_blks = (g.N + BN - 1) / BN;
+  const int num_tiles = m_blks * n_blks;
+  const int k_blks = (g.K + BK - 1) / BK;
+  const bool three = g.passes == 3;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_b_hi);
+    if (three) {
+      ptx::prefetch_tmap(&tm_a_lo);
+      ptx::prefetch_tmap(&tm_b_lo);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (three ? 4u : 2u) * TILE_BYTES;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mb = tile % m_blks, nb = tile / m_blks;
+        const int m0 = mb * BM, n0 = nb * BN;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
+          ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), k0, m0);
+            if (three) ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), k0, m0);
+          } else {  // stored [K, M]: two 64(M) x 64(K) boxes
+            ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), m0, k0);
+            ptx::tma_load_2d(sa_hi + TILE_BYTES / 2, &tm_a_hi, full_bar(stage), m0 + 64, k0);
+            if (three) {
+              ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), m0, k0);
+              ptx::tma_load_2d(sa_lo + TILE_BYTES / 2, &tm_a_lo, full_bar(stage), m0 + 64, k0);
+            }
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), k0, n0);
+            if (three) ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), k0, n0);
+          } else {
+            ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), n0, k0);
+            ptx::tma_load_2d(sb_hi + TILE_BYTES / 2, &tm_b_hi, full_bar(stage), n0 + 64, k0);
+            if (three) {
+              ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), n0, k0);
+              ptx::tma_load_2d(sb_lo + TILE_BYTES / 2, &tm_b_lo, full_bar(stage), n0 + 64, k0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the 128-B swizzle row.
+      // MN-major: 64-element chunks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), +2048 B per UMMA_K.
+      constexpr uint32_t A_LBO = A_MN ? 8192u : 16u, A_SBO = 1024u, A_KSTEP = A_MN ? 2048u : 32u;
+      constexpr uint32_t B_LBO = B_MN ? 8192u : 16u, B_SBO = 1024u, B_KSTEP = B_MN ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + k * A_KSTEP, A_LBO, A_SBO);
+            const uint64_t db_hi = ptx::make_smem_desc_sw128(sb_hi + k * B_KSTEP, B_LBO, B_SBO);
+            ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+            if (three) {
+              const uint64_t da_lo = ptx::make_smem_desc_sw128(sa_lo + k * A_KSTEP, A_LBO, A_SBO);
+              const uint64_t db_lo = ptx::make_smem_desc_sw128(sb_lo + k * B_KSTEP, B_LBO, B_SBO);
+              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mb = tile % m_blks, nb = tile / m_blks;
+      const int row = mb * BM + quad * 32 + lane;
+      const int n0 = nb * BN;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const bool row_ok = row < g.M;
+      const int64_t orow = row_ok ? (g.row_map ? (int64_t)g.row_map[row] : (int64_t)row) : 0;
+      float* crow = g.C + orow * g.ldc;
+      const float* brow = (g.bias_rows && row_ok) ? g.bias_rows + (int64_t)(row % g.bias_period) * g.N : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          const int cb = n0 + c * 32;
+          const bool vec = (cb + 32 <= g.N) && ((((uintptr_t)(crow + cb)) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              float* vp = &v.x;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float x = g.alpha * __uint_as_float(r[j + q]);
+                if (g.bias_n) x += g.bias_n[cb + j + q];
+                if (brow) x += brow[cb + j + q];
+                vp[q] = x;
+              }
+              float4* dst = (float4*)(crow + cb + j);
+              if (g.beta != 0.f) {
+                const float4 o = *dst;
+                v.x += g.beta * o.x; v.y += g.beta * o.y; v.z += g.beta * o.z; v.w += g.beta * o.w;
+              }
+              *dst = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb + j;
+              if (col < g.N) {
+                float x = g.alpha * __uint_as_float(r[j]);
+                if (g.bias_n) x += g.bias_n[col];
+                if (brow) x += brow[col];
+                if (g.beta != 0.f) x += g.beta * crow[col];
+                crow[col] = x;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap* tm, const GemmArgs& g, int grid, cudaStream_t st) {
+  auto kern = k_gemm_tc<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    LV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], g);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M, int N, int K, int passes,
+            float alpha, float beta, const float* bias_n, const float* bias_rows, int bias_period,
+            const int32_t* out_row_map, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return LAGVAE_OK;
+  LV_CHECK_ARG(K > 0, "gemm_tc: K must be > 0");
+  LV_CHECK_ARG(passes == 1 || passes == 3, "gemm_tc: passes must be 1 or 3");
+  LV_CHECK_ARG(A.hi && B.hi && (passes == 1 || (A.lo && B.lo)), "gemm_tc: missing operand part");
+  LV_CHECK_ARG(bias_rows == nullptr || bias_period > 0, "gemm_tc: bias_period");
+  CUtensorMap tm[4];
+  // K-major operand: tensor [rows=MN, cols=K], box 64(K) x 128(rows).
+  // MN-major operand: tensor [rows=K, cols=MN], box 64(MN) x 64(K rows).
+  const void* parts[4] = {A.hi, passes == 3 ? A.lo : A.hi, B.hi, passes == 3 ? B.lo : B.hi};
+  for (int i = 0; i < 4; ++i) {
+    const bool isA = i < 2;
+    const TcOperand& o = isA ? A : B;
+    const uint64_t mn = isA ? M : N;
+    if (!o.mn_major)
+      LV_TRY(make_tmap_bf16_2d(&tm[i], parts[i], mn, K, o.ld, BK, isA ? BM : BN));
+    else
+      LV_TRY(make_tmap_bf16_2d(&tm[i], parts[i], K, mn, o.ld, 64, BK));
+  }
+  GemmArgs g{C, ldc, M, N, K, passes, alpha, beta, bias_n, bias_rows, bias_period, out_row_map};
+  const int tiles = (int)(cdiv(M, BM) * cdiv(N, BN));
+  const int grid = std::min(tiles, num_sms());
+  if (!A.mn_major && !B.mn_major) return launch<false, false>(tm, g, grid, st);
+  if (!A.mn_major && B.mn_major) return launch<false, true>(tm, g, grid, st);
+  if (A.mn_major && !B.mn_major) return launch<true, false>(tm, g, grid, st);
+  return launch<true, true>(tm, g, grid, st);
+}
+
+}  // namespace lagvae

@@ -1,0 +1,651 @@
+// Text-path plan: workspace carving and the launch sequence of VAE.loss forward / backward /
+// fused inner step.  Host-side C++ only; every arithmetic stage is a kernel in
+// kernels_simt.cu / gemm_tc.cu / lstm_tc.cu.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+#include "lstm_tc.cuh"
+
+using namespace lagvae;
+
+// parameter slots (reference state_dict order)
+enum { E_EMB = 0, E_WIH, E_WHH, E_BIH, E_BHH, E_LIN, D_EMB, D_TRANS, D_WIH, D_WHH, D_BIH, D_BHH, D_PRED };
+
+struct Mat {  // stored row-major fp32 matrix
+  const float* p;
+  int64_t rows, cols, ld;
+};
+struct Staged {
+  Mat m;
+  TcOperand tc;  // valid when tc.hi != nullptr
+};
+
+struct lagvae_text_plan {
+  lagvae_text_dims d;
+  uint32_t flags;
+  bool use_tc;
+  int Bd, Te, Td;
+  int64_t re, rd;
+  char* base;
+  size_t bytes;
+  // forward stash
+  float *xe, *gates_e, *c_e, *h_e, *bsum_e, *mu, *logvar, *z, *kl, *eps;
+  float *xd, *zb, *bsum_d, *c0, *h0, *gates_d, *c_d, *h_d, *hdrop_d, *logits, *lse, *loss_row, *scalars;
+  // backward scratch
+  float *g_rec, *g_kl, *dh_d, *dgates_d, *dx_d, *dc, *dh_rec, *dzb, *dc0t, *dz, *dml, *dh_last;
+  float *dgates_e, *dx_e, *dc_e, *dh_rec_e;
+  void* clip_scratch;
+  // tensor-core operand arena (bf16 hi/lo staging), bump allocated per pass
+  char* arena;
+  size_t arena_bytes, arena_off;
+  LstmTcState* lstm_tc;  // persistent tcgen05 LSTM state (nullptr when unsupported / SIMT)
+  // state carried from forward to backward
+  lagvae_dropout drop;
+  float kl_weight;
+  bool have_forward;
+};
+
+namespace {
+
+struct Carver {
+  char* base;
+  size_t off;
+  template <class T>
+  T* take(int64_t n) {
+    off = (size_t)round_up((int64_t)off, 256);
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += (size_t)n * sizeof(T);
+    return p;
+  }
+};
+
+size_t arena_need(const lagvae_text_dims& d) {
+  // generous bound: every staged operand of the backward pass (the larger pass), hi+lo bf16
+  const int64_t Bd = (int64_t)d.B * d.ns, re = (int64_t)d.T * d.B, rd = (int64_t)(d.T - 1) * Bd;
+  auto pad8 = [](int64_t c) { return round_up(c, 8); };
+  int64_t el = 0;
+  el += rd * pad8(d.V);                        // dlogits
+  el += (int64_t)d.V * pad8(d.nh);             // W_pred
+  el += 2 * rd * pad8(d.nh);                   // hdrop, h_d
+  el += rd * pad8(4 * d.nh) + rd * pad8(d.ni); // dgates_d, xd
+  el += re * pad8(4 * d.nh) + re * pad8(d.ni) + re * pad8(d.nh);  // dgates_e, xe, h_e
+  el += 2 * ((int64_t)4 * d.nh * pad8(d.ni + d.nz) + (int64_t)4 * d.nh * pad8(d.nh));  // LSTM weights
+  el += Bd * pad8(d.nh) * 4;
+  return (size_t)el * 2 * sizeof(uint16_t) + (64 << 10);
+}
+
+void carve(lagvae_text_plan* P, char* base) {
+  const lagvae_text_dims& d = P->d;
+  const int64_t B = d.B, Bd = P->Bd, re = P->re, rd = P->rd, nh = d.nh, ni = d.ni, nz = d.nz, V = d.V;
+  Carver c{base, 0};
+  P->xe = c.take<float>(re * ni);
+  P->gates_e = c.take<float>(re * 4 * nh);
+  P->c_e = c.take<float>(re * nh);
+  P->h_e = c.take<float>(re * nh);
+  P->bsum_e = c.take<float>(4 * nh);
+  P->mu = c.take<float>(B * nz);
+  P->logvar = c.take<float>(B * nz);
+  P->z = c.take<float>(Bd * nz);
+  P->kl = c.take<float>(B);
+  P->eps = c.take<float>(Bd * nz);
+  P->xd = c.take<float>(rd * ni);
+  P->zb = c.take<float>(Bd * 4 * nh);
+  P->bsum_d = c.take<float>(4 * nh);
+  P->c0 = c.take<float>(Bd * nh);
+  P->h0 = c.take<float>(Bd * nh);
+  P->gates_d = c.take<float>(rd * 4 * nh);
+  P->c_d = c.take<float>(rd * nh);
+  P->h_d = c.take<float>(rd * nh);
+  P->hdrop_d = c.take<float>(rd * nh);
+  P->logits = c.take<float>(rd * V);
+  P->lse = c.take<float>(rd);
+  P->loss_row = c.take<float>(rd);
+  P->scalars = c.take<float>(8);
+  P->g_rec = c.take<float>(B);
+  P->g_kl = c.take<float>(B);
+  P->dh_d = c.take<float>(rd * nh);
+  P->dgates_d = c.take<float>(rd * 4 * nh);
+  P->dx_d = c.take<float>(rd * ni);
+  P->dc = c.take<float>(Bd * nh);
+  P->dh_rec = c.take<float>(Bd * nh);
+  P->dzb = c.take<float>(Bd * 4 * nh);
+  P->dc0t = c.take<float>(Bd * nh);
+  P->dz = c.take<float>(Bd * nz);
+  P->dml = c.take<float>(B * 2 * nz);
+  P->dh_last = c.take<float>(B * nh);
+  P->dgates_e = c.take<float>(re * 4 * nh);
+  P->dx_e = c.take<float>(re * ni);
+  P->dc_e = c.take<float>(B * nh);
+  P->dh_rec_e = c.take<float>(B * nh);
+  P->clip_scratch = c.take<char>(4096);
+  P->arena_bytes = P->use_tc ? arena_need(d) : 0;
+  P->arena = c.take<char>((int64_t)P->arena_bytes);
+  c.off = (size_t)round_up((int64_t)c.off, 256);
+  P->bytes = c.off;
+}
+
+bool dims_ok(const lagvae_text_dims* d) {
+  return d && d->B > 0 && d->T >= 2 && d->ns > 0 && d->V > 1 && d->ni > 0 && d->nh > 0 && d->nz > 0;
+}
+
+bool want_tc(const lagvae_text_dims& d, uint32_t flags) {
+  if (flags & LAGVAE_PLAN_FORCE_SIMT) return false;
+  // the tcgen05 path pays off (and is validated) for tensor-core sized problems only
+  return d.nh >= 64 && d.ni >= 32 && d.V >= 128;
+}
+
+Staged stage(lagvae_text_plan* P, Mat m, cudaStream_t st, int* status) {
+  Staged s;
+  s.m = m;
+  s.tc = TcOperand{nullptr, nullptr, 0, 0};
+  if (!P->use_tc) return s;
+  const int64_t ldo = round_up(m.cols, 8);
+  const size_t need = (size_t)m.rows * ldo * sizeof(uint16_t);
+  size_t off = (size_t)round_up((int64_t)P->arena_off, 256);
+  if (off + 2 * need + 512 > P->arena_bytes) {
+    set_error("text plan: tensor-core staging arena exhausted");
+    *status = LAGVAE_E_WORKSPACE;
+    return s;
+  }
+  uint16_t* hi = (uint16_t*)(P->arena + off);
+  off = (size_t)round_up((int64_t)(off + need), 256);
+  uint16_t* lo = (uint16_t*)(P->arena + off);
+  P->arena_off = off + need;
+  const int r = split_bf16_launch(m.p, m.ld, (int)m.rows, (int)m.cols, hi, lo, ldo, st);
+  if (r != LAGVAE_OK) *status = r;
+  s.tc = TcOperand{hi, lo, ldo, 0};
+  return s;
+}
+
+// C[M,N] = alpha * opA · opBᵀ (+beta C)(+bias).  A used as [M,K]: stored [M,K] (a_t = false) or
+// stored [K,M] (a_t = true).  B used as [N,K]: stored [N,K] (b_t = false) or stored [K,N].
+int mm(lagvae_text_plan* P, const Staged& A, bool a_t, const Staged& B, bool b_t, float* C, int64_t ldc,
+       int M, int N, int K, float alpha, float beta, const float* bias_n, const float* bias_rows,
+       int bias_period, int passes, cudaStream_t st) {
+  const bool tc_ok = P->use_tc && A.tc.hi && B.tc.hi && M >= 32 && N >= 16 && K >= 16;
+  if (tc_ok) {
+    TcOperand a = A.tc, b = B.tc;
+    a.mn_major = a_t ? 1 : 0;
+    b.mn_major = b_t ? 1 : 0;
+    return gemm_tc(a, b, C, ldc, M, N, K, passes, alpha, beta, bias_n, bias_rows, bias_period, nullptr, st);
+  }
+  return gemm_f32(A.m.p, a_t ? 1 : A.m.ld, a_t ? A.m.ld : 1, B.m.p, b_t ? 1 : B.m.ld, b_t ? B.m.ld : 1, C,
+                  ldc, M, N, K, alpha, beta, bias_n, bias_rows, bias_period, st);
+}
+// sub-view of a staged matrix: rows [r0, r0+nr), cols [c0, c0+nc) (c0 multiple of 8 for tc)
+Staged sub(const Staged& s, int64_t r0, int64_t nr, int64_t c0, int64_t nc) {
+  Staged o = s;
+  o.m.p = s.m.p + r0 * s.m.ld + c0;
+  o.m.rows = nr;
+  o.m.cols = nc;
+  if (s.tc.hi) {
+    if (c0 % 8 != 0) {
+      o.tc.hi = o.tc.lo = nullptr;
+    } else {
+      o.tc.hi = s.tc.hi + r0 * s.tc.ld + c0;
+      o.tc.lo = s.tc.lo + r0 * s.tc.ld + c0;
+    }
+  }
+  return o;
+}
+
+DropSpec spec_in(const lagvae_dropout& d) {
+  DropSpec s{};
+  const bool on = d.mode != 0 && d.p_in > 0.f;
+  s.mode = on ? d.mode : 0;
+  s.p = d.p_in;
+  s.scale = on ? 1.f / (1.f - d.p_in) : 1.f;
+  s.mask = d.mask_in;
+  s.seed = d.seed;
+  s.sid = 1;
+  return s;
+}
+DropSpec spec_out(const lagvae_dropout& d) {
+  DropSpec s{};
+  const bool on = d.mode != 0 && d.p_out > 0.f;
+  s.mode = on ? d.mode : 0;
+  s.p = d.p_out;
+  s.scale = on ? 1.f / (1.f - d.p_out) : 1.f;
+  s.mask = d.mask_out;
+  s.seed = d.seed;
+  s.sid = 2;
+  return s;
+}
+DropSpec spec_none() {
+  DropSpec s{};
+  s.mode = 0;
+  s.scale = 1.f;
+  return s;
+}
+
+// ---- LSTM recurrence, launch-per-step tier (fp32 SIMT GEMM + point-wise cell) -------------------
+// gates [Tn*Bd, 4nh] holds the input projection on entry, activated gates on exit.
+int lstm_forward_steps(const float* w_hh, const float* h0, const float* c0, float* gates, float* c_all,
+                       float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd, int nh,
+                       cudaStream_t st) {
+  const int64_t gs = (int64_t)Bd * 4 * nh, hs = (int64_t)Bd * nh;
+  for (int t = 0; t < Tn; ++t) {
+    const float* hp = t ? h_all + (t - 1) * hs : h0;
+    const float* cp = t ? c_all + (t - 1) * hs : c0;
+    if (hp)
+      LV_TRY(gemm_f32(hp, nh, 1, w_hh, nh, 1, gates + t * gs, 4 * nh, Bd, 4 * nh, nh, 1.f, 1.f, nullptr,
+                      nullptr, 0, st));
+    LV_TRY(lstm_point_fwd(gates + t * gs, cp, c_all + t * hs, h_all + t * hs,
+                          hdrop_all ? hdrop_all + t * hs : nullptr, drop, t, Tn, Bd, nh, st));
+  }
+  return LAGVAE_OK;
+}
+// dh_ext: [Tn*Bd, nh] gradient wrt the emitted h (scaled by `drop` keep factors) or nullptr;
+// dh_last: [Bd, nh] extra gradient on the final h only (encoder) or nullptr.
+// On exit dc holds d c_{-1} and dh_rec holds d h_{-1} (when want_init).
+int lstm_backward_steps(const float* w_hh, const float* c0, const float* gates, const float* c_all,
+                        const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
+                        float* dh_rec, float* dgates, int Tn, int Bd, int nh, bool want_init,
+                        cudaStream_t st) {
+  const int64_t gs = (int64_t)Bd * 4 * nh, hs = (int64_t)Bd * nh;
+  LV_TRY(fill(dc, 0.f, hs, st));
+  for (int t = Tn - 1; t >= 0; --t) {
+    const float* ext = dh_ext ? dh_ext + t * hs : (t == Tn - 1 ? dh_last : nullptr);
+    const DropSpec ds = dh_ext ? drop : spec_none();
+    const float* cp = t ? c_all + (t - 1) * hs : c0;
+    LV_TRY(lstm_point_bwd(gates + t * gs, c_all + t * hs, cp, ext, ds, t == Tn - 1 ? nullptr : dh_rec, dc,
+                          dgates + t * gs, t, Tn, Bd, nh, st));
+    if (t > 0 || want_init)  // dh_{t-1} = dG_t · W_hh
+      LV_TRY(gemm_f32(dgates + t * gs, 4 * nh, 1, w_hh, 1, nh, dh_rec, nh, Bd, nh, 4 * nh, 1.f, 0.f, nullptr,
+                      nullptr, 0, st));
+  }
+  return LAGVAE_OK;
+}
+
+int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, cudaStream_t st) {
+  const lagvae_text_dims& d = P->d;
+  const int nh = d.nh, ni = d.ni;
+  int status = LAGVAE_OK;
+  LV_TRY(embed_gather(x, d.T, 0, d.B, 1, P->Te, w->p[E_EMB], ni, spec_none(), P->xe, st));   // enc_lstm.py:58
+  LV_TRY(vec_add(w->p[E_BIH], w->p[E_BHH], P->bsum_e, 4 * nh, st));
+  if (P->lstm_tc) {
+    LV_TRY(lstm_tc_pack_weights(P->lstm_tc, 0, w->p[E_WIH], ni, ni, w->p[E_WHH], st));
+  }
+  Staged sx = stage(P, Mat{P->xe, P->re, ni, ni}, st, &status);
+  Staged sw = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
+  LV_TRY(status);
+  // input projection for all steps (first half of nn.LSTM, enc_lstm.py:60)
+  LV_TRY(mm(P, sx, false, sw, false, P->gates_e, 4 * nh, (int)P->re, 4 * nh, ni, 1.f, 0.f, P->bsum_e, nullptr,
+            0, 3, st));
+  if (P->lstm_tc)
+    LV_TRY(lstm_tc_forward(P->lstm_tc, 0, nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
+                           P->Te, d.B, st));
+  else
+    LV_TRY(lstm_forward_steps(w->p[E_WHH], nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
+                              P->Te, d.B, nh, st));
+  return LAGVAE_OK;
+}
+
+
+// decoder forward up to per-token CE (dec_lstm.py:66-148).  z: device [Bd, nz].
+int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, const float* z,
+                    const lagvae_dropout& dr, cudaStream_t st) {
+  const lagvae_text_dims& d = P->d;
+  const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td;
+  int status = LAGVAE_OK;
+  // ---- decoder: dec_lstm.py:66-111
+  const DropSpec din = spec_in(dr), dout = spec_out(dr);
+  LV_TRY(embed_gather(x, d.T, 0, B, ns, Td, w->p[D_EMB], ni, din, P->xd, st));                // :80-81 (+:87-91)
+  LV_TRY(vec_add(w->p[D_BIH], w->p[D_BHH], P->bsum_d, 4 * nh, st));
+  // z enters every step through the last nz input columns (:84,97): time-invariant row bias
+  LV_TRY(gemm_f32(z, nz, 1, w->p[D_WIH] + ni, ni + nz, 1, P->zb, 4 * nh, Bd, 4 * nh, nz, 1.f, 0.f,
+                  P->bsum_d, nullptr, 0, st));
+  LV_TRY(gemm_f32(z, nz, 1, w->p[D_TRANS], nz, 1, P->c0, nh, Bd, nh, nz, 1.f, 0.f, nullptr, nullptr, 0,
+                  st));                                                                      // :100
+  LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
+  if (P->lstm_tc) LV_TRY(lstm_tc_pack_weights(P->lstm_tc, 1, w->p[D_WIH], ni, ni + nz, w->p[D_WHH], st));
+  Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
+  Staged swd = stage(P, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
+  LV_TRY(status);
+  LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
+            3, st));
+  float* hdrop = dout.mode ? P->hdrop_d : nullptr;
+  if (P->lstm_tc)
+    LV_TRY(lstm_tc_forward(P->lstm_tc, 1, P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st));
+  else
+    LV_TRY(lstm_forward_steps(w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, nh,
+                              st));                                                          // :104,106
+  // vocabulary projection (:109) + cross entropy (:143-148)
+  Staged sh = stage(P, Mat{hdrop ? hdrop : P->h_d, P->rd, nh, nh}, st, &status);
+  Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
+  LV_TRY(status);
+  LV_TRY(mm(P, sh, false, swp, false, P->logits, V, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  LV_TRY(ce_fwd(P->logits, V, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
+  return LAGVAE_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int lagvae_abi_version(void) { return LAGVAE_ABI_VERSION; }
+const char* lagvae_last_error(void) { return lagvae::last_error(); }
+int64_t lagvae_launch_count(void) { return lagvae::g_launches.load(); }
+
+int lagvae_device_check(void) {
+  int dev = 0;
+  LV_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  LV_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("lagvae: device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major,
+              prop.minor);
+    return LAGVAE_E_CUDA;
+  }
+  return LAGVAE_OK;
+}
+
+int64_t lagvae_text_param_count(const lagvae_text_dims* d) {
+  if (!dims_ok(d)) return -1;
+  const int64_t V = d->V, ni = d->ni, nh = d->nh, nz = d->nz;
+  return V * ni + 4 * nh * ni + 4 * nh * nh + 8 * nh + 2 * nz * nh      // encoder
+         + V * ni + nh * nz + 4 * nh * (ni + nz) + 4 * nh * nh + 8 * nh + V * nh;  // decoder
+}
+
+size_t lagvae_text_workspace_bytes(const lagvae_text_dims* d, uint32_t flags) {
+  if (!dims_ok(d)) return 0;
+  lagvae_text_plan P{};
+  P.d = *d;
+  P.flags = flags;
+  P.use_tc = want_tc(*d, flags);
+  P.Bd = d->B * d->ns;
+  P.Te = d->T;
+  P.Td = d->T - 1;
+  P.re = (int64_t)P.Te * d->B;
+  P.rd = (int64_t)P.Td * P.Bd;
+  carve(&P, nullptr);
+  return P.bytes + lstm_tc_workspace_bytes(*d, P.use_tc);
+}
+
+int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* workspace,
+                            size_t workspace_bytes, lagvae_text_plan** out) {
+  LV_CHECK_ARG(dims_ok(d), "text plan: bad dims");
+  LV_CHECK_ARG(out != nullptr && workspace != nullptr, "text plan: null workspace/out");
+  LV_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "text plan: workspace must be 256-B aligned");
+  const size_t need = lagvae_text_workspace_bytes(d, flags);
+  if (workspace_bytes < need) {
+    set_error("text plan: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return LAGVAE_E_WORKSPACE;
+  }
+  LV_TRY(lagvae_device_check());
+  lagvae_text_plan* P = new (std::nothrow) lagvae_text_plan{};
+  LV_CHECK_ARG(P != nullptr, "text plan: host allocation failed");
+  P->d = *d;
+  P->flags = flags;
+  P->use_tc = want_tc(*d, flags);
+  P->Bd = d->B * d->ns;
+  P->Te = d->T;
+  P->Td = d->T - 1;
+  P->re = (int64_t)P->Te * d->B;
+  P->rd = (int64_t)P->Td * P->Bd;
+  P->base = (char*)workspace;
+  carve(P, P->base);
+  P->lstm_tc = nullptr;
+  const int r = lstm_tc_create(*d, P->use_tc, P->base + P->bytes, workspace_bytes - P->bytes, &P->lstm_tc);
+  if (r != LAGVAE_OK) {
+    delete P;
+    return r;
+  }
+  P->have_forward = false;
+  *out = P;
+  return LAGVAE_OK;
+}
+
+void lagvae_text_plan_destroy(lagvae_text_plan* P) {
+  if (!P) return;
+  lstm_tc_destroy(P->lstm_tc);
+  delete P;
+}
+
+int lagvae_text_encode_stats(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                             float* out_mu, float* out_logvar, void* stream) {
+  LV_CHECK_ARG(P && w && x && out_mu && out_logvar, "encode_stats: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  P->arena_off = 0;
+  P->have_forward = false;
+  LV_TRY(encoder_forward(P, w, x, st));
+  const float* h_last = P->h_e + (int64_t)(P->Te - 1) * P->d.B * P->d.nh;
+  LV_TRY(head_reparam_kl(h_last, w->p[E_LIN], nullptr, P->d.B, P->d.nh, P->d.nz, 1, out_mu, out_logvar,
+                         nullptr, nullptr, st));
+  return LAGVAE_OK;
+}
+
+int lagvae_text_loss_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                             const float* eps, float kl_weight, const lagvae_dropout* drop,
+                             float* out_loss, float* out_rec, float* out_kl, float* out_mu,
+                             float* out_logvar, float* out_z, void* stream) {
+  LV_CHECK_ARG(P && w && x && eps && out_loss && out_rec && out_kl, "loss_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const lagvae_text_dims& d = P->d;
+  const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td;
+  lagvae_dropout dr{};
+  if (drop) dr = *drop;
+  LV_CHECK_ARG(dr.mode >= 0 && dr.mode <= 2, "loss_forward: bad dropout mode");
+  LV_CHECK_ARG(dr.mode != 1 || ((dr.p_in <= 0.f || dr.mask_in) && (dr.p_out <= 0.f || dr.mask_out)),
+               "loss_forward: dropout mode 1 needs masks");
+  LV_CHECK_ARG(dr.p_in < 1.f && dr.p_out < 1.f, "loss_forward: dropout p must be < 1");
+  P->drop = dr;
+  P->kl_weight = kl_weight;
+  P->arena_off = 0;
+  P->have_forward = false;
+  int status = LAGVAE_OK;
+
+  // ---- encoder: enc_lstm.py:47-64 ; reparameterise + KL: encoder.py:40-79
+  LV_TRY(encoder_forward(P, w, x, st));
+  LV_CUDA(cudaMemcpyAsync(P->eps, eps, sizeof(float) * Bd * nz, cudaMemcpyDeviceToDevice, st));
+  const float* h_last = P->h_e + (int64_t)(P->Te - 1) * B * nh;
+  LV_TRY(head_reparam_kl(h_last, w->p[E_LIN], P->eps, B, nh, nz, ns, P->mu, P->logvar, P->z, P->kl, st));
+
+  LV_TRY(decoder_forward(P, w, x, P->z, dr, st));
+  LV_TRY(finalize_loss(P->loss_row, P->kl, B, ns, Td, kl_weight, out_loss, out_rec, out_kl, P->scalars, st));
+  if (out_mu) LV_CUDA(cudaMemcpyAsync(out_mu, P->mu, sizeof(float) * B * nz, cudaMemcpyDeviceToDevice, st));
+  if (out_logvar)
+    LV_CUDA(cudaMemcpyAsync(out_logvar, P->logvar, sizeof(float) * B * nz, cudaMemcpyDeviceToDevice, st));
+  if (out_z) LV_CUDA(cudaMemcpyAsync(out_z, P->z, sizeof(float) * Bd * nz, cudaMemcpyDeviceToDevice, st));
+  P->have_forward = true;
+  return LAGVAE_OK;
+}
+
+int lagvae_text_reconstruct_error(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                                  const float* z, const lagvae_dropout* drop, float* out_rec_rows,
+                                  void* stream) {
+  LV_CHECK_ARG(P && w && x && z && out_rec_rows, "reconstruct_error: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  lagvae_dropout dr{};
+  if (drop) dr = *drop;
+  LV_CHECK_ARG(dr.mode >= 0 && dr.mode <= 2 && dr.p_in < 1.f && dr.p_out < 1.f, "reconstruct_error: bad dropout");
+  P->arena_off = 0;
+  P->have_forward = false;
+  LV_TRY(decoder_forward(P, w, x, z, dr, st));
+  LV_TRY(time_sum(P->loss_row, P->Td, P->Bd, 1, out_rec_rows, st));   // dec_lstm.py:148
+  return LAGVAE_OK;
+}
+
+int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                              const float* g_loss, const float* g_rec, const float* g_kl,
+                              const lagvae_text_params* gr, void* stream) {
+  LV_CHECK_ARG(P && w && x && gr, "loss_backward: null argument");
+  LV_CHECK_ARG(P->have_forward, "loss_backward: no forward stash on this plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const lagvae_text_dims& d = P->d;
+  const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td, Te = P->Te;
+  const int64_t re = P->re, rd = P->rd;
+  const DropSpec din = spec_in(P->drop), dout = spec_out(P->drop);
+  int status = LAGVAE_OK;
+  P->arena_off = 0;
+  P->have_forward = false;  // logits are consumed in place
+
+  LV_TRY(combine_upstream(g_loss, g_rec, g_kl, P->kl_weight, B, P->g_rec, P->g_kl, st));
+
+  // ---- CE + vocabulary projection backward (autograd of dec_lstm.py:109,143-148)
+  LV_TRY(ce_bwd(P->logits, V, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, st));
+  const float* hd = dout.mode ? P->hdrop_d : P->h_d;
+  {
+    Staged sdl = stage(P, Mat{P->logits, rd, V, V}, st, &status);
+    Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
+    Staged sh = stage(P, Mat{hd, rd, nh, nh}, st, &status);
+    LV_TRY(status);
+    // dH_drop [rd, nh] = dlogits · W_pred
+    LV_TRY(mm(P, sdl, false, swp, true, P->dh_d, nh, (int)rd, nh, V, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    // dW_pred [V, nh] = dlogitsᵀ · H_drop
+    LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  }
+  P->arena_off = 0;  // dlogits staging no longer needed
+
+  // ---- decoder LSTM backward (cuDNN RNN backward in the reference)
+  if (P->lstm_tc)
+    LV_TRY(lstm_tc_backward(P->lstm_tc, 1, P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc, P->dh_rec,
+                            P->dgates_d, Td, Bd, true, st));
+  else
+    LV_TRY(lstm_backward_steps(w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc,
+                               P->dh_rec, P->dgates_d, Td, Bd, nh, true, st));
+  LV_TRY(time_sum(P->dgates_d, Td, Bd, 4 * nh, P->dzb, st));
+  LV_TRY(col_sum(P->dzb, Bd, 4 * nh, gr->p[D_BIH], gr->p[D_BHH], st));
+  {
+    Staged sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
+    Staged sxd = stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
+    Staged shd = stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
+    Staged swx = stage(P, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
+    LV_TRY(status);
+    // dW_ih[:, :ni] = dGᵀ · X   ;  dW_ih[:, ni:] = dzbᵀ · z
+    LV_TRY(mm(P, sdg, true, sxd, true, gr->p[D_WIH], ni + nz, 4 * nh, ni, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
+              3, st));
+    LV_TRY(gemm_f32(P->dzb, 1, 4 * nh, P->z, 1, nz, gr->p[D_WIH] + ni, ni + nz, 4 * nh, nz, Bd, 1.f, 0.f, nullptr,
+                    nullptr, 0, st));
+    // dW_hh = Σ_t dG_tᵀ h_{t-1}: rows t>=1 pair with h_d[t-1]; t=0 pairs with h0
+    if (Td > 1)
+      LV_TRY(mm(P, sub(sdg, Bd, rd - Bd, 0, 4 * nh), true, sub(shd, 0, rd - Bd, 0, nh), true, gr->p[D_WHH], nh,
+                4 * nh, nh, (int)(rd - Bd), 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    LV_TRY(gemm_f32(P->dgates_d, 1, 4 * nh, P->h0, 1, nh, gr->p[D_WHH], nh, 4 * nh, nh, Bd, 1.f,
+                    Td > 1 ? 1.f : 0.f, nullptr, nullptr, 0, st));
+    // dX = dG · W_ih[:, :ni]  -> dense decoder embedding gradient (row V-1 = padding_idx, no grad)
+    LV_TRY(mm(P, sdg, false, swx, true, P->dx_d, ni, (int)rd, ni, 4 * nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  }
+  LV_TRY(fill(gr->p[D_EMB], 0.f, (int64_t)V * ni, st));
+  LV_TRY(embed_scatter_add(x, d.T, 0, B, ns, Td, P->dx_d, ni, din, gr->p[D_EMB], V - 1, st));
+  // initial state: c0 = z W_transᵀ, h0 = tanh(c0)  (dec_lstm.py:100-101)
+  LV_TRY(dc0_total(P->dc, P->dh_rec, P->h0, P->dc0t, Bd * nh, st));
+  LV_TRY(gemm_f32(P->dc0t, 1, nh, P->z, 1, nz, gr->p[D_TRANS], nz, nh, nz, Bd, 1.f, 0.f, nullptr, nullptr, 0, st));
+  // dz = dzb · W_ih[:, ni:] + dc0_tot · W_trans
+  LV_TRY(gemm_f32(P->dzb, 4 * nh, 1, w->p[D_WIH] + ni, 1, ni + nz, P->dz, nz, Bd, nz, 4 * nh, 1.f, 0.f, nullptr,
+                  nullptr, 0, st));
+  LV_TRY(gemm_f32(P->dc0t, nh, 1, w->p[D_TRANS], 1, nz, P->dz, nz, Bd, nz, nh, 1.f, 1.f, nullptr, nullptr, 0, st));
+
+  // ---- reparameterisation + KL + head backward
+  LV_TRY(reparam_kl_bwd(P->dz, P->eps, P->mu, P->logvar, P->g_kl, B, nz, ns, P->dml, st));
+  const float* h_last = P->h_e + (int64_t)(Te - 1) * B * nh;
+  LV_TRY(gemm_f32(P->dml, 2 * nz, 1, w->p[E_LIN], 1, nh, P->dh_last, nh, B, nh, 2 * nz, 1.f, 0.f, nullptr,
+                  nullptr, 0, st));
+  LV_TRY(gemm_f32(P->dml, 1, 2 * nz, h_last, 1, nh, gr->p[E_LIN], nh, 2 * nz, nh, B, 1.f, 0.f, nullptr, nullptr,
+                  0, st));
+
+  // ---- encoder LSTM backward
+  P->arena_off = 0;
+  if (P->lstm_tc)
+    LV_TRY(lstm_tc_backward(P->lstm_tc, 0, nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
+                            P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, false, st));
+  else
+    LV_TRY(lstm_backward_steps(w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
+                               P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, nh, false, st));
+  LV_TRY(col_sum(P->dgates_e, (int)re, 4 * nh, gr->p[E_BIH], gr->p[E_BHH], st));
+  {
+    Staged sdg = stage(P, Mat{P->dgates_e, re, 4 * nh, 4 * nh}, st, &status);
+    Staged sxe = stage(P, Mat{P->xe, re, ni, ni}, st, &status);
+    Staged she = stage(P, Mat{P->h_e, re, nh, nh}, st, &status);
+    Staged swx = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
+    LV_TRY(status);
+    LV_TRY(mm(P, sdg, true, sxe, true, gr->p[E_WIH], ni, 4 * nh, ni, (int)re, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    if (Te > 1)
+      LV_TRY(mm(P, sub(sdg, B, re - B, 0, 4 * nh), true, sub(she, 0, re - B, 0, nh), true, gr->p[E_WHH], nh,
+                4 * nh, nh, (int)(re - B), 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    else
+      LV_TRY(fill(gr->p[E_WHH], 0.f, (int64_t)4 * nh * nh, st));
+    LV_TRY(mm(P, sdg, false, swx, true, P->dx_e, ni, (int)re, ni, 4 * nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  }
+  LV_TRY(fill(gr->p[E_EMB], 0.f, (int64_t)V * ni, st));
+  LV_TRY(embed_scatter_add(x, d.T, 0, B, 1, Te, P->dx_e, ni, spec_none(), gr->p[E_EMB], -1, st));
+  return LAGVAE_OK;
+}
+
+int lagvae_clip_sgd_step(float* const* h_params, float* const* h_grads, const int64_t* h_counts, int n_seg,
+                         int n_update, float max_norm, float lr, int scale_all_grads, float* out_norm,
+                         void* scratch, void* stream) {
+  LV_CHECK_ARG(h_grads && h_counts && scratch && (n_update == 0 || h_params), "clip_sgd_step: null argument");
+  return clip_sgd_step(h_params, h_grads, h_counts, n_seg, n_update, max_norm, lr, scale_all_grads, out_norm,
+                       scratch, (cudaStream_t)stream);
+}
+
+int lagvae_mi_estimate(const float* mu, const float* logvar, const float* eps, int B, int nz, float* out_mi,
+                       void* stream) {
+  LV_CHECK_ARG(mu && logvar && eps && out_mi && B > 0 && nz > 0, "mi_estimate: bad argument");
+  return mi_estimate(mu, logvar, eps, B, nz, out_mi, (cudaStream_t)stream);
+}
+
+int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                           const float* eps, float kl_weight, const lagvae_dropout* drop, float max_norm,
+                           float lr, float* grad_ws, float* out_loss, float* out_scalars, void* stream) {
+  LV_CHECK_ARG(P && w && x && eps && grad_ws && out_loss && out_scalars, "inner_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const lagvae_text_dims& d = P->d;
+  const int64_t V = d.V, ni = d.ni, nh = d.nh, nz = d.nz;
+  const int64_t counts[LAGVAE_TEXT_NPARAM] = {V * ni, 4 * nh * ni, 4 * nh * nh, 4 * nh, 4 * nh, 2 * nz * nh,
+                                              V * ni, nh * nz, 4 * nh * (ni + nz), 4 * nh * nh, 4 * nh, 4 * nh,
+                                              V * nh};
+  lagvae_text_params g;
+  int64_t off = 0;
+  for (int i = 0; i < LAGVAE_TEXT_NPARAM; ++i) {
+    g.p[i] = grad_ws + off;
+    off += counts[i];
+  }
+  // text.py:379 loss; :381 Σloss; :382 mean(dim=-1) -> upstream 1/B
+  LV_TRY(lagvae_text_loss_forward(P, w, x, eps, kl_weight, drop, out_loss, P->dml /*rec tmp*/, P->dh_last /*kl tmp*/,
+                                  nullptr, nullptr, nullptr, stream));
+  LV_CUDA(cudaMemcpyAsync(out_scalars, P->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  LV_TRY(fill(P->dc0t, 1.f / (float)d.B, d.B, st));
+  LV_TRY(lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, stream));
+  // text.py:385 clip over all 13 grads; :387 encoder-only SGD step
+  LV_TRY(clip_sgd_step(w->p, g.p, counts, LAGVAE_TEXT_NPARAM, 6, max_norm, lr, 0, out_scalars + 3,
+                       P->clip_scratch, st));
+  return LAGVAE_OK;
+}
+
+int lagvae_gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                    float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, const float* bias_n,
+                    const float* bias_rows, int bias_period, void* stream) {
+  LV_CHECK_ARG(A && B && C, "gemm_f32: null argument");
+  return gemm_f32(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, alpha, beta, bias_n, bias_rows, bias_period,
+                  (cudaStream_t)stream);
+}
+
+int lagvae_gemm_tc(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, int a_mn_major,
+                   const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int b_mn_major, float* C,
+                   int64_t ldc, int M, int N, int K, int passes, float alpha, float beta, const float* bias_n,
+                   const float* bias_rows, int bias_period, const int32_t* out_row_map, void* stream) {
+  LV_CHECK_ARG(A_hi && B_hi && C, "gemm_tc: null argument");
+  TcOperand a{A_hi, A_lo, lda, a_mn_major}, b{B_hi, B_lo, ldb, b_mn_major};
+  return gemm_tc(a, b, C, ldc, M, N, K, passes, alpha, beta, bias_n, bias_rows, bias_period, out_row_map,
+                 (cudaStream_t)stream);
+}
+
+int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
+                      int64_t ld_out, void* stream) {
+  LV_CHECK_ARG(src && hi && lo && ld_out >= cols, "split_bf16: bad argument");
+  return split_bf16_launch(src, ld, rows, cols, hi, lo, ld_out, (cudaStream_t)stream);
+}
+
+int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep, void* stream) {
+  LV_CHECK_ARG(out_keep && n >= 0, "dropout_mask: bad argument");
+  return dropout_mask(seed, stream_id, n, p, out_keep, (cudaStream_t)stream);
+}
+
+}  // extern "C"

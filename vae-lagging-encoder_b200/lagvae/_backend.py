@@ -1,0 +1,101 @@
+"""ctypes binding of liblagvae.so (the C-ABI declared in include/lagvae.h).
+
+There is no CPU fallback: importing this module without the built library, or calling a compute
+entry point without a B200 (sm_100) CUDA device, raises.  PyTorch is used by callers only for
+device memory and streams; nothing here takes torch types.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblagvae.so")
+
+OK, E_ARG, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
+ABI_VERSION = 1
+NPARAM = 13
+PLAN_DEFAULT, PLAN_FORCE_SIMT, PLAN_INFERENCE = 0, 1, 2
+
+
+class LagvaeError(RuntimeError):
+    pass
+
+
+class TextDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("ns", C.c_int32), ("V", C.c_int32),
+                ("ni", C.c_int32), ("nh", C.c_int32), ("nz", C.c_int32)]
+
+
+class TextParams(C.Structure):
+    _fields_ = [("p", C.c_void_p * NPARAM)]
+
+
+class Dropout(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("p_in", C.c_float), ("p_out", C.c_float),
+                ("mask_in", C.c_void_p), ("mask_out", C.c_void_p), ("seed", C.c_uint64)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/lagvae.h (tests check this)
+_vp, _i, _f, _i64, _u32, _u64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint32, C.c_uint64, C.c_size_t
+PROTOTYPES = {
+    "lagvae_abi_version": (_i, []),
+    "lagvae_last_error": (C.c_char_p, []),
+    "lagvae_device_check": (_i, []),
+    "lagvae_launch_count": (_i64, []),
+    "lagvae_text_workspace_bytes": (_sz, [C.POINTER(TextDims), _u32]),
+    "lagvae_text_plan_create": (_i, [C.POINTER(TextDims), _u32, _vp, _sz, C.POINTER(_vp)]),
+    "lagvae_text_plan_destroy": (None, [_vp]),
+    "lagvae_text_loss_forward": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_text_loss_backward": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _vp, _vp,
+                                       C.POINTER(TextParams), _vp]),
+    "lagvae_text_encode_stats": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _vp, _vp]),
+    "lagvae_text_reconstruct_error": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, C.POINTER(Dropout), _vp, _vp]),
+    "lagvae_clip_sgd_step": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _f, _f, _i,
+                                  _vp, _vp, _vp]),
+    "lagvae_mi_estimate": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "lagvae_text_param_count": (_i64, [C.POINTER(TextDims)]),
+    "lagvae_text_inner_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f,
+                                    _vp, _vp, _vp, _vp]),
+    "lagvae_gemm_f32": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp]),
+    "lagvae_gemm_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _f, _f,
+                            _vp, _vp, _i, _vp, _vp]),
+    "lagvae_split_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i64, _vp]),
+    "lagvae_dropout_mask": (_i, [_u64, _u32, _i64, _f, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes library; raises LagvaeError when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LagvaeError(
+                "liblagvae.so is not built (%s). Run `python vae-lagging-encoder_b200/build.py` "
+                "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if a declared symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if L.lagvae_abi_version() != ABI_VERSION:
+            raise LagvaeError("liblagvae.so ABI %d != binding ABI %d" % (L.lagvae_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(status, what=""):
+    if status != OK:
+        msg = lib().lagvae_last_error()
+        raise LagvaeError("%s failed (status %d): %s" % (what or "lagvae call", status,
+                                                         msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(lib().lagvae_launch_count())
