@@ -169,6 +169,23 @@ int lagvae_gemm_tc(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, int 
                    const float* bias_n, const float* bias_rows, int bias_period,
                    const int32_t* out_row_map, void* stream);
 
+/* LSTM recurrence of nn.LSTM (enc_lstm.py:60 / dec_lstm.py:104) given the input projection.
+ * tier 0: launch-per-step fp32 SIMT; tier 1: persistent tcgen05 kernel (one cooperative launch for all
+ * Tn steps; needs nh % 8 == 0, nh/8 <= #SMs, Bd <= 512 and a workspace of lagvae_lstm_workspace_bytes).
+ *  gates [Tn*Bd, 4nh]: pre-activations (x W_ihᵀ + b) on entry, activated i,f,g,o on exit (the stash);
+ *  h0/c0 [Bd,nh] or NULL (zeros); c_all/h_all [Tn*Bd,nh]; hdrop_all (or NULL) = h * dropout_out keep/scale
+ *  (uses drop->p_out / mask_out / seed).  Backward: dh_ext [Tn*Bd,nh] gradient wrt the emitted h (scaled by
+ *  the same dropout) or NULL; dh_last [Bd,nh] gradient on the final h or NULL; on exit dgates [Tn*Bd,4nh],
+ *  dc = d c_{-1}, dh_rec = d h_{-1} (when want_init). */
+size_t lagvae_lstm_workspace_bytes(int nh, int Bd);
+int lagvae_lstm_forward(int tier, int nh, int Tn, int Bd, const float* w_hh, const float* h0,
+                        const float* c0, float* gates, float* c_all, float* h_all, float* hdrop_all,
+                        const lagvae_dropout* drop, void* workspace, size_t workspace_bytes, void* stream);
+int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, const float* c0,
+                         const float* gates, const float* c_all, const float* dh_ext, const float* dh_last,
+                         const lagvae_dropout* drop, float* dc, float* dh_rec, float* dgates, int want_init,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* fp32 [rows, cols] (ld) -> bf16 hi/lo [rows, ld_out] (zero padded columns cols..ld_out). */
 int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, void* stream);

@@ -141,7 +141,8 @@ def test_mi_estimate_matches_oracle():
         mu, lv, eps = torch.randn(B, nz), 0.3 * torch.randn(B, nz), torch.randn(B, 1, nz)
         want = O.calc_mi_from_stats(mu.double(), lv.double(), eps.double())
         out = torch.empty(1, device="cuda")
-        be.check(be.lib().lagvae_mi_estimate(be.ptr(mu.cuda()), be.ptr(lv.cuda()), be.ptr(eps.cuda()), B, nz, be.ptr(out), _st()))
+        mu_d, lv_d, eps_d = mu.cuda(), lv.cuda(), eps.cuda()      # keep the device tensors alive across the launch
+        be.check(be.lib().lagvae_mi_estimate(be.ptr(mu_d), be.ptr(lv_d), be.ptr(eps_d), B, nz, be.ptr(out), _st()))
         assert abs(float(out) - want) <= 1e-4 * max(1.0, abs(want)), (float(out), want)
 
 
@@ -166,3 +167,42 @@ def test_clip_sgd_matches_torch():
         for p, rp, g in zip(ps, ref_p, gs):
             assert float((p - rp.detach()).abs().max()) < 1e-6 * max(1.0, float(rp.abs().max()))
             assert float((g - rp.grad).abs().max()) < 1e-6 * max(1.0, float(rp.grad.abs().max()))
+
+
+@pytest.mark.parametrize("nh,Bd,Tn,init,dropout", [(128, 16, 5, True, True), (1024, 32, 6, False, False),
+                                                    (1024, 32, 4, True, True), (192, 70, 4, True, False),
+                                                    (64, 5, 3, False, True), (512, 130, 3, True, True)])
+def test_lstm_persistent_tcgen05_matches_step_tier(nh, Bd, Tn, init, dropout):
+    """Persistent tcgen05 recurrence (one cooperative launch) vs the launch-per-step fp32 tier."""
+    be = _be()
+    g = torch.Generator(device="cuda").manual_seed(nh + Bd)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    w_hh = (torch.rand(4 * nh, nh, generator=g, device="cuda") * 2 - 1) * (3.0 / nh ** 0.5)
+    pre = rn(Tn * Bd, 4 * nh)
+    h0 = torch.tanh(rn(Bd, nh)) if init else None
+    c0 = rn(Bd, nh) if init else None
+    mask = (torch.rand(Bd, Tn, nh, generator=g, device="cuda") > 0.5).to(torch.uint8).contiguous()
+    drop = be.Dropout()
+    drop.mode, drop.p_in, drop.p_out, drop.mask_out = (1 if dropout else 0), 0.0, 0.5, mask.data_ptr()
+    ws = torch.zeros(int(be.lib().lagvae_lstm_workspace_bytes(nh, Bd)), dtype=torch.uint8, device="cuda")
+    dh_ext = rn(Tn * Bd, nh) * 0.1
+    dh_last = rn(Bd, nh) * 0.1
+    res = []
+    for tier in (0, 1):
+        gates = pre.clone()
+        c_all, h_all, hd = torch.zeros(Tn * Bd, nh, device="cuda"), torch.zeros(Tn * Bd, nh, device="cuda"), torch.zeros(Tn * Bd, nh, device="cuda")
+        be.check(be.lib().lagvae_lstm_forward(tier, nh, Tn, Bd, be.ptr(w_hh), be.ptr(h0), be.ptr(c0), be.ptr(gates), be.ptr(c_all),
+                                              be.ptr(h_all), be.ptr(hd) if dropout else None, C.byref(drop), be.ptr(ws), ws.numel(), _st()),
+                 "lstm_forward tier %d" % tier)
+        torch.cuda.synchronize()
+        dc, dhr, dg = torch.zeros(Bd, nh, device="cuda"), torch.zeros(Bd, nh, device="cuda"), torch.zeros(Tn * Bd, 4 * nh, device="cuda")
+        be.check(be.lib().lagvae_lstm_backward(tier, nh, Tn, Bd, be.ptr(w_hh), be.ptr(c0), be.ptr(gates), be.ptr(c_all), be.ptr(dh_ext),
+                                               be.ptr(dh_last), C.byref(drop), be.ptr(dc), be.ptr(dhr), be.ptr(dg), 1, be.ptr(ws),
+                                               ws.numel(), _st()), "lstm_backward tier %d" % tier)
+        torch.cuda.synchronize()
+        res.append((gates, c_all, h_all, hd, dg, dc, dhr))
+    names = ["gates", "c", "h", "hdrop", "dgates", "dc_init", "dh_init"]
+    for n, a, b in zip(names, res[1], res[0]):
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-20))
+        assert err < 2e-4, "%s: rel err %.3e" % (n, err)
+    assert float(res[0][2].abs().max()) > 0.05   # the comparison is not vacuous

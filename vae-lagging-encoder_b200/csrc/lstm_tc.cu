@@ -1,27 +1,554 @@
-// Persistent tcgen05 LSTM recurrence — placeholder translation unit (kernel lands in a later commit).
+// Persistent LSTM recurrence on tcgen05 (sm_100a): ONE launch runs all T time steps of the forward
+// (or backward) recurrence of nn.LSTM (enc_lstm.py:60, dec_lstm.py:104 and their cuDNN backward).
+//
+// Decomposition (nh = 1024 -> 128 CTAs, one per SM, co-resident via cooperative launch):
+//   forward : CTA c owns hidden units [8c, 8c+8)  = 32 gate columns (i,f,g,o x 8).  Its W_hh slice
+//             [32 x nh] lives in shared memory for the whole kernel as split-bf16 (hi, lo) UMMA
+//             B-operand tiles (128 KiB at nh = 1024).  Per step the previous hidden state h_{t-1}
+//             [Bd x nh] (bf16 hi/lo, written by all CTAs) is streamed through a cp.async.cg ring
+//             (L2 only) as the A operand; tcgen05.mma M=64 x N=32 x K=16 accumulates in TMEM
+//             (hi*hi + hi*lo + lo*hi, fp32).  Four epilogue warps read TMEM (tcgen05.ld), add the
+//             input projection, apply the gate non-linearities and the cell update in fp32, and
+//             publish h_t (fp32 stash + bf16 hi/lo for the next step).
+//   backward: CTA c owns the same 8 units; resident operand = W_hhᵀ slice [8 x 4nh] (128 KiB);
+//             streamed operand = dG_{t+1} [Bd x 4nh] (bf16 hi/lo); UMMA M=64 x N=8.
+//   One grid-wide barrier (atomic counter, release/acquire) separates time steps.
+// Rows of the 64-row UMMA tile beyond the batch are zero (never written) — TMEM layout for M=64:
+// row i -> lane 32*(i/16) + i%16 (cute/atom/mma_traits_sm100.hpp, tmem_frg M_MMA == 64).
 #include "lstm_tc.cuh"
+#include "sm100_ptx.cuh"
+
+#include <new>
 
 namespace lagvae {
 
-size_t lstm_tc_workspace_bytes(const lagvae_text_dims&, bool) { return 0; }
-int lstm_tc_create(const lagvae_text_dims&, bool, void*, size_t, LstmTcState** out) {
+namespace {
+
+constexpr int NTHREADS = 288;             // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
+constexpr int NPROD = 128;
+constexpr int A_PART = 64 * 128;          // 8 KiB: 64 rows x 128 B (64 bf16 of K)
+constexpr int STAGE_BYTES = 2 * A_PART;   // hi + lo
+constexpr int LAG = 4;                    // cp.async groups in flight behind the newest one
+constexpr int MAX_MT = 8;                 // m-tiles of 64 batch rows (Bd <= 512)
+constexpr int SMEM_LIMIT = 232448;        // 227 KiB
+
+struct RecArgs {
+  int nh, Bd, Tn, KP, KB, NS, m_tiles;
+  unsigned* bar;                 // grid barrier counter (host-zeroed)
+  __nv_bfloat16* abuf;           // [2 slots][2 parts][Bd][KP] streamed operand (h or dG), bf16 hi/lo
+  const float* w_hh;             // [4nh, nh]
+  // forward
+  const float* h0;
+  const float* c0;
+  float* gates;                  // [Tn*Bd, 4nh] pre-activations in, activated out
+  float* c_all;
+  float* h_all;
+  float* hdrop_all;
+  DropSpec drop;
+  // backward
+  const float* dh_ext;           // [Tn*Bd, nh] or null
+  const float* dh_last;          // [Bd, nh] or null
+  float* dc;                     // [Bd, nh]
+  float* dh_rec_out;             // [Bd, nh] (d h_{-1}) when want_init
+  float* dgates;                 // [Tn*Bd, 4nh]
+  int want_init;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// cooperative-groups style grid barrier on a monotonically increasing counter
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_u32(bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void tmem_alloc_rt(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// swizzled (SWIZZLE_128B, K-major) byte offset of 16-byte chunk c of row r inside a tile of 128-B rows
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct Smem {
+  uint32_t w_base, a_base, bar_base;
+  __device__ uint32_t full(int s) const { return bar_base + 8u * s; }
+  __device__ uint32_t empty(int s, int NS) const { return bar_base + 8u * (NS + s); }
+  __device__ uint32_t acc(int mt, int NS) const { return bar_base + 8u * (2 * NS + mt); }
+  __device__ uint32_t tmem_slot(int NS) const { return bar_base + 8u * (2 * NS + MAX_MT); }
+};
+
+// ---- producer: stream rows [mt*64, ...) of the current slot through the ring -------------------
+struct PipeState {
+  int stage;
+  uint32_t phase;
+};
+
+template <int WTILE_BYTES>
+__device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, PipeState& ps,
+                                              const __nv_bfloat16* slot, int mt, int ptid) {
+  const int rows = min(64, a.Bd - mt * 64);
+  const int per_part = rows * 8;
+  const int64_t part_stride = (int64_t)a.Bd * a.KP;
+  int sig_stage = ps.stage;  // stage of the oldest un-signalled group
+  for (int kb = 0; kb < a.KB + LAG; ++kb) {
+    if (kb < a.KB) {
+      ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
+      const uint32_t sbase = sm.a_base + ps.stage * STAGE_BYTES;
+      for (int id = ptid; id < 2 * per_part; id += NPROD) {
+        const int part = id >= per_part;
+        const int rem = id - part * per_part;
+        const int r = rem >> 3, c = rem & 7;
+        const __nv_bfloat16* src = slot + part * part_stride + (int64_t)(mt * 64 + r) * a.KP + kb * 64 + c * 8;
+        ptx::cp_async_cg16(sbase + part * A_PART + sw128(r, c), src);
+      }
+      if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+    }
+    ptx::cp_async_commit();
+    if (kb >= LAG) {  // group kb-LAG has landed for this thread
+      ptx::cp_async_wait<LAG>();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(sm.full(sig_stage));
+      if (++sig_stage == a.NS) sig_stage = 0;
+    }
+  }
+  ptx::cp_async_wait<0>();
+}
+
+// ---- MMA issuer: one K sweep for m-tile mt ------------------------------------------------------
+template <int NB>
+__device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeState& ps, uint32_t d_tmem,
+                                         uint32_t acc_bar) {
+  constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(64, NB, 0, 0);
+  constexpr int WT = NB * 128;  // bytes of one weight tile (NB rows x 128 B)
+  for (int kb = 0; kb < a.KB; ++kb) {
+    ptx::mbar_wait(sm.full(ps.stage), ps.phase);
+    ptx::tc_fence_after();
+    const uint32_t sa = sm.a_base + ps.stage * STAGE_BYTES;
+    const uint32_t sw = sm.w_base + (uint32_t)(kb * 2) * WT;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+      const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + A_PART + k * 32, 16, 1024);
+      const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
+      const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
+      ptx::umma_f16(d_tmem, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+      ptx::umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+      ptx::umma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+    }
+    ptx::umma_commit(sm.empty(ps.stage, a.NS));
+    if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+  }
+  ptx::umma_commit(acc_bar);
+}
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[8]) {
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
+  *(uint4*)dst_hi = *(const uint4*)hi;
+  *(uint4*)dst_lo = *(const uint4*)lo;
+}
+
+__device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm, int tmem_cols, uint32_t* slot_ptr) {
+  const int warp = threadIdx.x >> 5;
+  // zero the ring (rows beyond the batch must read as zero)
+  for (int i = threadIdx.x; i < a.NS * STAGE_BYTES / 16; i += NTHREADS)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sm.a_base + i * 16), "r"(0u) : "memory");
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.NS; ++s) {
+      ptx::mbar_init(sm.full(s), NPROD);
+      ptx::mbar_init(sm.empty(s, a.NS), 1);
+    }
+    for (int m = 0; m < MAX_MT; ++m) ptx::mbar_init(sm.acc(m, a.NS), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc_rt(sm.tmem_slot(a.NS), (uint32_t)tmem_cols);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  (void)slot_ptr;
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int NB = 32, WT = NB * 128;
+  Smem sm;
+  sm.w_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  sm.a_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
+  sm.bar_base = sm.a_base + (uint32_t)a.NS * STAGE_BYTES;
+  uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = a.nh, Bd = a.Bd, u0 = blockIdx.x * 8;
+  const int tmem_cols = a.m_tiles * 32 <= 32 ? 32 : (a.m_tiles * 32 <= 64 ? 64 : (a.m_tiles * 32 <= 128 ? 128 : 256));
+
+  // resident W_hh slice: tile (kb, part) = [32 rows x 64 k] bf16, rows n = gate*8 + uu
+  for (int id = threadIdx.x; id < 32 * (a.KP / 8); id += NTHREADS) {
+    const int n = id / (a.KP / 8), ck = id % (a.KP / 8);
+    const int k0 = ck * 8;
+    const float* src = a.w_hh + (int64_t)((n >> 3) * nh + u0 + (n & 7)) * nh + k0;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < nh) ? src[j] : 0.f;
+    const int kb = k0 >> 6, c = (k0 & 63) >> 3;
+    uint8_t* t_hi = gen_base + (size_t)(kb * 2) * WT + sw128(n, c);
+    store_bf16x8((__nv_bfloat16*)t_hi, (__nv_bfloat16*)(t_hi + WT), v);
+  }
+  common_prologue(a, sm, tmem_cols, nullptr);
+  const uint32_t tmem_base = *(uint32_t*)(gen_base + (sm.tmem_slot(a.NS) - sm.w_base));
+
+  // publish h_{-1} (own 8 units, all rows) into slot 1
+  const int64_t slot_elems = (int64_t)2 * Bd * a.KP;
+  for (int b = threadIdx.x; b < Bd; b += NTHREADS) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = a.h0 ? a.h0[(int64_t)b * nh + u0 + j] : 0.f;
+    __nv_bfloat16* d = a.abuf + slot_elems + (int64_t)b * a.KP + u0;
+    store_bf16x8(d, d + (int64_t)Bd * a.KP, v);
+  }
+  unsigned epoch = 0;
+  grid_barrier(a.bar, (++epoch) * gridDim.x);
+
+  PipeState ps{0, 0};
+  for (int t = 0; t < a.Tn; ++t) {
+    const __nv_bfloat16* rd = a.abuf + (int64_t)((t + 1) & 1) * slot_elems;
+    __nv_bfloat16* wr = a.abuf + (int64_t)(t & 1) * slot_elems;
+    if (warp >= 5) {
+      for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
+    } else if (warp == 4) {
+      if (lane == 0)
+        for (int mt = 0; mt < a.m_tiles; ++mt)
+          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32), sm.acc(mt, a.NS));
+      __syncwarp();
+    } else {
+      float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
+      for (int mt = 0; mt < a.m_tiles; ++mt) {
+        const int b = mt * 64 + warp * 16 + lane;
+        const bool valid = lane < 16 && b < Bd;
+        float pre[32], cp[8];
+        if (valid) {  // prefetch the input projection and c_{t-1} while the MMAs run
+          const float* g = gates_t + (int64_t)b * 4 * nh + u0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 x0 = *(const float4*)(g + q * nh), x1 = *(const float4*)(g + q * nh + 4);
+            pre[q * 8 + 0] = x0.x; pre[q * 8 + 1] = x0.y; pre[q * 8 + 2] = x0.z; pre[q * 8 + 3] = x0.w;
+            pre[q * 8 + 4] = x1.x; pre[q * 8 + 5] = x1.y; pre[q * 8 + 6] = x1.z; pre[q * 8 + 7] = x1.w;
+          }
+          const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + u0 : (a.c0 ? a.c0 + (int64_t)b * nh + u0 : nullptr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp[j] = cpp ? cpp[j] : 0.f;
+        }
+        ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)(t & 1));
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 32), r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float hv[8], cv[8], act[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ig = sigmoidf_(pre[j] + __uint_as_float(r[j]));
+            const float fg = sigmoidf_(pre[8 + j] + __uint_as_float(r[8 + j]));
+            const float gg = tanhf(pre[16 + j] + __uint_as_float(r[16 + j]));
+            const float og = sigmoidf_(pre[24 + j] + __uint_as_float(r[24 + j]));
+            const float c = fg * cp[j] + ig * gg;
+            cv[j] = c;
+            hv[j] = og * tanhf(c);
+            act[j] = ig; act[8 + j] = fg; act[16 + j] = gg; act[24 + j] = og;
+          }
+          float* g = gates_t + (int64_t)b * 4 * nh + u0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *(float4*)(g + q * nh) = make_float4(act[q * 8], act[q * 8 + 1], act[q * 8 + 2], act[q * 8 + 3]);
+            *(float4*)(g + q * nh + 4) = make_float4(act[q * 8 + 4], act[q * 8 + 5], act[q * 8 + 6], act[q * 8 + 7]);
+          }
+          const int64_t o = ((int64_t)t * Bd + b) * nh + u0;
+          *(float4*)(a.c_all + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          *(float4*)(a.c_all + o + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+          *(float4*)(a.h_all + o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *(float4*)(a.h_all + o + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          if (a.hdrop_all) {
+            float hd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hd[j] = hv[j] * drop_factor(a.drop, ((uint64_t)b * a.Tn + t) * nh + u0 + j);
+            *(float4*)(a.hdrop_all + o) = make_float4(hd[0], hd[1], hd[2], hd[3]);
+            *(float4*)(a.hdrop_all + o + 4) = make_float4(hd[4], hd[5], hd[6], hd[7]);
+          }
+          __nv_bfloat16* d = wr + (int64_t)b * a.KP + u0;
+          store_bf16x8(d, d + (int64_t)Bd * a.KP, hv);
+        }
+      }
+      ptx::tc_fence_before();
+    }
+    grid_barrier(a.bar, (++epoch) * gridDim.x);
+    ptx::tc_fence_after();
+  }
+  if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int NB = 8, WT = NB * 128;
+  Smem sm;
+  sm.w_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  sm.a_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
+  sm.bar_base = sm.a_base + (uint32_t)a.NS * STAGE_BYTES;
+  uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = a.nh, Bd = a.Bd, Tn = a.Tn, u0 = blockIdx.x * 8;
+  const int tmem_cols = a.m_tiles * 8 <= 32 ? 32 : 64;
+
+  // resident W_hhᵀ slice: rows n = unit uu, K index = gate column k in [0, 4nh): W_hh[k, u0+uu]
+  for (int id = threadIdx.x; id < 8 * (a.KP / 8); id += NTHREADS) {
+    const int n = id % 8, ck = id / 8;   // consecutive threads -> consecutive units (32-B segments of a W_hh row)
+    const int k0 = ck * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < 4 * nh) ? a.w_hh[(int64_t)(k0 + j) * nh + u0 + n] : 0.f;
+    const int kb = k0 >> 6, c = (k0 & 63) >> 3;
+    uint8_t* t_hi = gen_base + (size_t)(kb * 2) * WT + sw128(n, c);
+    store_bf16x8((__nv_bfloat16*)t_hi, (__nv_bfloat16*)(t_hi + WT), v);
+  }
+  common_prologue(a, sm, tmem_cols, nullptr);
+  const uint32_t tmem_base = *(uint32_t*)(gen_base + (sm.tmem_slot(a.NS) - sm.w_base));
+  for (int i = threadIdx.x; i < Bd * 8; i += NTHREADS) a.dc[(int64_t)(i >> 3) * nh + u0 + (i & 7)] = 0.f;
+  __syncthreads();
+
+  const int64_t slot_elems = (int64_t)2 * Bd * a.KP;
+  unsigned epoch = 0;
+  PipeState ps{0, 0};
+  const int nsteps = Tn + (a.want_init ? 1 : 0);
+  for (int s = 0; s < nsteps; ++s) {
+    const int t = Tn - 1 - s;            // t = -1 on the extra step that only produces d h_{-1}
+    const bool has_rec = s > 0;
+    const __nv_bfloat16* rd = a.abuf + (int64_t)((s + 1) & 1) * slot_elems;
+    __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
+    if (warp >= 5) {
+      if (has_rec)
+        for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
+    } else if (warp == 4) {
+      if (has_rec && lane == 0)
+        for (int mt = 0; mt < a.m_tiles; ++mt)
+          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8), sm.acc(mt, a.NS));
+      __syncwarp();
+    } else {
+      for (int mt = 0; mt < a.m_tiles; ++mt) {
+        const int b = mt * 64 + warp * 16 + lane;
+        const bool valid = lane < 16 && b < Bd;
+        float gt[32], cc[8], cp[8], dcv[8], dhx[8];
+        if (valid && t >= 0) {
+          const float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + u0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 x0 = *(const float4*)(g + q * nh), x1 = *(const float4*)(g + q * nh + 4);
+            gt[q * 8 + 0] = x0.x; gt[q * 8 + 1] = x0.y; gt[q * 8 + 2] = x0.z; gt[q * 8 + 3] = x0.w;
+            gt[q * 8 + 4] = x1.x; gt[q * 8 + 5] = x1.y; gt[q * 8 + 6] = x1.z; gt[q * 8 + 7] = x1.w;
+          }
+          const int64_t o = ((int64_t)t * Bd + b) * nh + u0;
+          const float* cpp = t ? a.c_all + o - (int64_t)Bd * nh : (a.c0 ? a.c0 + (int64_t)b * nh + u0 : nullptr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cc[j] = a.c_all[o + j];
+            cp[j] = cpp ? cpp[j] : 0.f;
+            dcv[j] = a.dc[(int64_t)b * nh + u0 + j];
+            float e = 0.f;
+            if (a.dh_ext) e = a.dh_ext[o + j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + u0 + j);
+            if (t == Tn - 1 && a.dh_last) e += a.dh_last[(int64_t)b * nh + u0 + j];
+            dhx[j] = e;
+          }
+        }
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0u;
+        if (has_rec) {
+          ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)((s - 1) & 1));
+          ptx::tc_fence_after();
+          tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 8), r);
+          ptx::tmem_ld_wait();
+        }
+        if (valid) {
+          if (t < 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a.dh_rec_out[(int64_t)b * nh + u0 + j] = __uint_as_float(r[j]);
+          } else {
+            float dg[32], dcn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float ig = gt[j], fg = gt[8 + j], gg = gt[16 + j], og = gt[24 + j];
+              const float dh = __uint_as_float(r[j]) + dhx[j];
+              const float tc = tanhf(cc[j]);
+              const float dct = dcv[j] + dh * og * (1.f - tc * tc);
+              dg[j] = dct * gg * ig * (1.f - ig);
+              dg[8 + j] = dct * cp[j] * fg * (1.f - fg);
+              dg[16 + j] = dct * ig * (1.f - gg * gg);
+              dg[24 + j] = dh * tc * og * (1.f - og);
+              dcn[j] = dct * fg;
+            }
+            float* go = a.dgates + ((int64_t)t * Bd + b) * 4 * nh + u0;
+            __nv_bfloat16* wb = wr + (int64_t)b * a.KP + u0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *(float4*)(go + q * nh) = make_float4(dg[q * 8], dg[q * 8 + 1], dg[q * 8 + 2], dg[q * 8 + 3]);
+              *(float4*)(go + q * nh + 4) = make_float4(dg[q * 8 + 4], dg[q * 8 + 5], dg[q * 8 + 6], dg[q * 8 + 7]);
+              float seg[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) seg[j] = dg[q * 8 + j];
+              store_bf16x8(wb + q * nh, wb + q * nh + (int64_t)Bd * a.KP, seg);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a.dc[(int64_t)b * nh + u0 + j] = dcn[j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+    grid_barrier(a.bar, (++epoch) * gridDim.x);
+    ptx::tc_fence_after();
+  }
+  if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct LstmTcState {
+  int nh, G, KPf, KPb, NSf, NSb, max_bd;
+  size_t smem_f, smem_b;
+  __nv_bfloat16* abuf;
+  unsigned* bar;
+  bool configured;
+};
+
+static bool shape_supported(const lagvae_text_dims& d, int* nsf, int* nsb, size_t* smf, size_t* smb) {
+  const int nh = d.nh;
+  if (nh % 8 != 0 || nh < 64) return false;
+  int sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (nh / 8 > sms) return false;
+  if ((int64_t)d.B * d.ns > 64 * MAX_MT) return false;
+  const int KPf = (int)round_up(nh, 64), KPb = (int)round_up(4 * nh, 64);
+  const int64_t wf = (int64_t)(KPf / 64) * 2 * 32 * 128, wb = (int64_t)(KPb / 64) * 2 * 8 * 128;
+  const int64_t misc = 1024 + 8 * (2 * 8 + MAX_MT) + 64;
+  const int nf = (int)std::min<int64_t>(8, (SMEM_LIMIT - wf - misc) / STAGE_BYTES);
+  const int nb = (int)std::min<int64_t>(8, (SMEM_LIMIT - wb - misc) / STAGE_BYTES);
+  if (nf < LAG + 1 || nb < LAG + 1) return false;
+  *nsf = nf;
+  *nsb = nb;
+  *smf = (size_t)(wf + (int64_t)nf * STAGE_BYTES + misc);
+  *smb = (size_t)(wb + (int64_t)nb * STAGE_BYTES + misc);
+  return true;
+}
+
+size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc) {
+  if (!use_tc) return 0;
+  const int64_t Bd = (int64_t)d.B * d.ns, KPb = round_up(4 * d.nh, 64);
+  return (size_t)(2 * 2 * Bd * KPb * 2 + 1024);   // sized for the backward operand (>= forward's)
+}
+
+int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_bytes, LstmTcState** out) {
   *out = nullptr;
+  if (!use_tc) return LAGVAE_OK;
+  int nsf = 0, nsb = 0;
+  size_t smf = 0, smb = 0;
+  if (!shape_supported(d, &nsf, &nsb, &smf, &smb)) return LAGVAE_OK;
+  if (ws_bytes < lstm_tc_workspace_bytes(d, true)) {
+    set_error("lstm_tc: workspace too small");
+    return LAGVAE_E_WORKSPACE;
+  }
+  LstmTcState* s = new (std::nothrow) LstmTcState{};
+  LV_CHECK_ARG(s != nullptr, "lstm_tc: host allocation failed");
+  s->nh = d.nh;
+  s->G = d.nh / 8;
+  s->KPf = (int)round_up(d.nh, 64);
+  s->KPb = (int)round_up(4 * d.nh, 64);
+  s->NSf = nsf;
+  s->NSb = nsb;
+  s->smem_f = smf;
+  s->smem_b = smb;
+  s->max_bd = d.B * d.ns;
+  s->bar = (unsigned*)ws;
+  s->abuf = (__nv_bfloat16*)((char*)ws + 1024);
+  s->configured = false;
+  *out = s;
   return LAGVAE_OK;
 }
-void lstm_tc_destroy(LstmTcState*) {}
-int lstm_tc_pack_weights(LstmTcState*, int, const float*, int, int64_t, const float*, cudaStream_t) {
-  set_error("lstm_tc: not available");
-  return LAGVAE_E_ARG;
+
+void lstm_tc_destroy(LstmTcState* s) { delete s; }
+
+static int configure(LstmTcState* s) {
+  if (s->configured) return LAGVAE_OK;
+  LV_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_f));
+  LV_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_b));
+  s->configured = true;
+  return LAGVAE_OK;
 }
-int lstm_tc_forward(LstmTcState*, int, const float*, const float*, float*, float*, float*, float*, DropSpec, int,
-                    int, cudaStream_t) {
-  set_error("lstm_tc: not available");
-  return LAGVAE_E_ARG;
+
+int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,
+                    float* c_all, float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd,
+                    cudaStream_t st) {
+  LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_forward: bad arguments");
+  LV_TRY(configure(s));
+  RecArgs a{};
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPf; a.KB = s->KPf / 64; a.NS = s->NSf;
+  a.m_tiles = (int)cdiv(Bd, 64);
+  a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
+  a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
+  LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
+  // the K padding columns of the streamed buffer must be zero
+  if (s->KPf != s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPf * 2, st));
+  void* args[] = {(void*)&a};
+  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, s->smem_f, st));
+  g_launches.fetch_add(1);
+  return LAGVAE_OK;
 }
-int lstm_tc_backward(LstmTcState*, int, const float*, const float*, const float*, const float*, DropSpec,
-                     const float*, float*, float*, float*, int, int, bool, cudaStream_t) {
-  set_error("lstm_tc: not available");
-  return LAGVAE_E_ARG;
+
+int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
+                     const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
+                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st) {
+  LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_backward: bad arguments");
+  LV_TRY(configure(s));
+  RecArgs a{};
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPb; a.KB = s->KPb / 64; a.NS = s->NSb;
+  a.m_tiles = (int)cdiv(Bd, 64);
+  a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
+  a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;
+  a.dh_rec_out = dh_rec; a.dgates = dgates; a.want_init = want_init ? 1 : 0;
+  LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
+  if (s->KPb != 4 * s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPb * 2, st));
+  void* args[] = {(void*)&a};
+  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, s->smem_b, st));
+  g_launches.fetch_add(1);
+  return LAGVAE_OK;
 }
 
 }  // namespace lagvae

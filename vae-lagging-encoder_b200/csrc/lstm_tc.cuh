@@ -7,16 +7,15 @@ namespace lagvae {
 struct LstmTcState;  // opaque; nullptr = not available for this shape -> launch-per-step tier
 
 size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc);
-// returns LAGVAE_OK with *out == nullptr when the shape is not covered by the persistent kernel
+// returns LAGVAE_OK with *out == nullptr when the shape is not covered by the persistent kernels
 int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_bytes, LstmTcState** out);
 void lstm_tc_destroy(LstmTcState* s);
-// which: 0 encoder, 1 decoder.  Packs W_hh (and keeps W_ih geometry) into the kernel's resident layout.
-int lstm_tc_pack_weights(LstmTcState* s, int which, const float* w_ih, int ni_cols, int64_t ld_ih,
-                         const float* w_hh, cudaStream_t st);
-int lstm_tc_forward(LstmTcState* s, int which, const float* h0, const float* c0, float* gates, float* c_all,
-                    float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd, cudaStream_t st);
-int lstm_tc_backward(LstmTcState* s, int which, const float* c0, const float* gates, const float* c_all,
-                     const float* dh_ext, DropSpec drop, const float* dh_last, float* dc, float* dh_rec,
-                     float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st);
+// Same contracts as lstm_forward_steps / lstm_backward_steps in text_plan.cu.
+int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,
+                    float* c_all, float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd,
+                    cudaStream_t st);
+int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
+                     const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
+                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st);
 
 }  // namespace lagvae

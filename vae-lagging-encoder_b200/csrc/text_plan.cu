@@ -265,9 +265,6 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   int status = LAGVAE_OK;
   LV_TRY(embed_gather(x, d.T, 0, d.B, 1, P->Te, w->p[E_EMB], ni, spec_none(), P->xe, st));   // enc_lstm.py:58
   LV_TRY(vec_add(w->p[E_BIH], w->p[E_BHH], P->bsum_e, 4 * nh, st));
-  if (P->lstm_tc) {
-    LV_TRY(lstm_tc_pack_weights(P->lstm_tc, 0, w->p[E_WIH], ni, ni, w->p[E_WHH], st));
-  }
   Staged sx = stage(P, Mat{P->xe, P->re, ni, ni}, st, &status);
   Staged sw = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
   LV_TRY(status);
@@ -275,7 +272,7 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   LV_TRY(mm(P, sx, false, sw, false, P->gates_e, 4 * nh, (int)P->re, 4 * nh, ni, 1.f, 0.f, P->bsum_e, nullptr,
             0, 3, st));
   if (P->lstm_tc)
-    LV_TRY(lstm_tc_forward(P->lstm_tc, 0, nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
+    LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[E_WHH], nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
                            P->Te, d.B, st));
   else
     LV_TRY(lstm_forward_steps(w->p[E_WHH], nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
@@ -300,7 +297,6 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   LV_TRY(gemm_f32(z, nz, 1, w->p[D_TRANS], nz, 1, P->c0, nh, Bd, nh, nz, 1.f, 0.f, nullptr, nullptr, 0,
                   st));                                                                      // :100
   LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
-  if (P->lstm_tc) LV_TRY(lstm_tc_pack_weights(P->lstm_tc, 1, w->p[D_WIH], ni, ni + nz, w->p[D_WHH], st));
   Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
   Staged swd = stage(P, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
   LV_TRY(status);
@@ -308,7 +304,7 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
             3, st));
   float* hdrop = dout.mode ? P->hdrop_d : nullptr;
   if (P->lstm_tc)
-    LV_TRY(lstm_tc_forward(P->lstm_tc, 1, P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st));
+    LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st));
   else
     LV_TRY(lstm_forward_steps(w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, nh,
                               st));                                                          // :104,106
@@ -504,7 +500,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
 
   // ---- decoder LSTM backward (cuDNN RNN backward in the reference)
   if (P->lstm_tc)
-    LV_TRY(lstm_tc_backward(P->lstm_tc, 1, P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc, P->dh_rec,
+    LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc, P->dh_rec,
                             P->dgates_d, Td, Bd, true, st));
   else
     LV_TRY(lstm_backward_steps(w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc,
@@ -552,7 +548,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   // ---- encoder LSTM backward
   P->arena_off = 0;
   if (P->lstm_tc)
-    LV_TRY(lstm_tc_backward(P->lstm_tc, 0, nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
+    LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
                             P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, false, st));
   else
     LV_TRY(lstm_backward_steps(w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
@@ -617,6 +613,67 @@ int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, con
   LV_TRY(clip_sgd_step(w->p, g.p, counts, LAGVAE_TEXT_NPARAM, 6, max_norm, lr, 0, out_scalars + 3,
                        P->clip_scratch, st));
   return LAGVAE_OK;
+}
+
+size_t lagvae_lstm_workspace_bytes(int nh, int Bd) {
+  lagvae_text_dims d{Bd, 2, 1, 2, 1, nh, 1};
+  return lstm_tc_workspace_bytes(d, true) + 256;
+}
+
+static int lstm_state_for(int tier, int nh, int Bd, void* ws, size_t ws_bytes, LstmTcState** st_out) {
+  *st_out = nullptr;
+  if (tier == 0) return LAGVAE_OK;
+  LV_CHECK_ARG(ws && ((uintptr_t)ws & 255) == 0, "lstm: tier 1 needs a 256-B aligned workspace");
+  lagvae_text_dims d{Bd, 2, 1, 2, 1, nh, 1};
+  LV_TRY(lstm_tc_create(d, true, ws, ws_bytes, st_out));
+  if (!*st_out) {
+    set_error("lstm: shape nh=%d Bd=%d is not covered by the persistent tcgen05 kernel", nh, Bd);
+    return LAGVAE_E_ARG;
+  }
+  return LAGVAE_OK;
+}
+
+int lagvae_lstm_forward(int tier, int nh, int Tn, int Bd, const float* w_hh, const float* h0, const float* c0,
+                        float* gates, float* c_all, float* h_all, float* hdrop_all, const lagvae_dropout* drop,
+                        void* ws, size_t ws_bytes, void* stream) {
+  LV_CHECK_ARG(w_hh && gates && c_all && h_all && nh > 0 && Tn > 0 && Bd > 0, "lstm_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  lagvae_dropout dr{};
+  if (drop) dr = *drop;
+  const DropSpec ds = hdrop_all ? spec_out(dr) : spec_none();
+  LstmTcState* s = nullptr;
+  LV_TRY(lstm_state_for(tier, nh, Bd, ws, ws_bytes, &s));
+  int r;
+  if (s) {
+    r = lstm_tc_forward(s, w_hh, h0, c0, gates, c_all, h_all, hdrop_all, ds, Tn, Bd, st);
+    lstm_tc_destroy(s);
+  } else {
+    r = lstm_forward_steps(w_hh, h0, c0, gates, c_all, h_all, hdrop_all, ds, Tn, Bd, nh, st);
+  }
+  return r;
+}
+
+int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, const float* c0,
+                         const float* gates, const float* c_all, const float* dh_ext, const float* dh_last,
+                         const lagvae_dropout* drop, float* dc, float* dh_rec, float* dgates, int want_init,
+                         void* ws, size_t ws_bytes, void* stream) {
+  LV_CHECK_ARG(w_hh && gates && c_all && dc && dh_rec && dgates && nh > 0 && Tn > 0 && Bd > 0,
+               "lstm_backward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  lagvae_dropout dr{};
+  if (drop) dr = *drop;
+  const DropSpec ds = dh_ext ? spec_out(dr) : spec_none();
+  LstmTcState* s = nullptr;
+  LV_TRY(lstm_state_for(tier, nh, Bd, ws, ws_bytes, &s));
+  int r;
+  if (s) {
+    r = lstm_tc_backward(s, w_hh, c0, gates, c_all, dh_ext, ds, dh_last, dc, dh_rec, dgates, Tn, Bd, want_init != 0, st);
+    lstm_tc_destroy(s);
+  } else {
+    r = lstm_backward_steps(w_hh, c0, gates, c_all, dh_ext, ds, dh_last, dc, dh_rec, dgates, Tn, Bd, nh,
+                            want_init != 0, st);
+  }
+  return r;
 }
 
 int lagvae_gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,

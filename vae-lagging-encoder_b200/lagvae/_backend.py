@@ -56,6 +56,10 @@ PROTOTYPES = {
     "lagvae_text_param_count": (_i64, [C.POINTER(TextDims)]),
     "lagvae_text_inner_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f,
                                     _vp, _vp, _vp, _vp]),
+    "lagvae_lstm_workspace_bytes": (_sz, [_i, _i]),
+    "lagvae_lstm_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _sz, _vp]),
+    "lagvae_lstm_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _vp, _i,
+                                  _vp, _sz, _vp]),
     "lagvae_gemm_f32": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp]),
     "lagvae_gemm_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _f, _f,
                             _vp, _vp, _i, _vp, _vp]),

@@ -56,6 +56,8 @@ class TextEngine:
         if self.device.type != "cuda":
             raise be.LagvaeError("lagvae kernels need a CUDA (B200, sm_100) device; got %r — "
                                  "there is no CPU fallback" % (device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.V, self.ni, self.nh, self.nz = int(V), int(ni), int(nh), int(nz)
         if force_simt is None:
             force_simt = os.environ.get("LAGVAE_FORCE_SIMT", "0") == "1"
