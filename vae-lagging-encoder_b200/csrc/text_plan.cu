@@ -2,6 +2,7 @@
 // fused inner step.  Host-side C++ only; every arithmetic stage is a kernel in
 // kernels_simt.cu / gemm_tc.cu / lstm_tc.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -387,7 +388,10 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
   P->base = (char*)workspace;
   carve(P, P->base);
   P->lstm_tc = nullptr;
-  const int r = lstm_tc_create(*d, P->use_tc, P->base + P->bytes, workspace_bytes - P->bytes, &P->lstm_tc);
+  // LAGVAE_NO_LSTM_TC=1 keeps the tensor-core GEMMs but runs the recurrence on the launch-per-step tier
+  const char* no_rec = getenv("LAGVAE_NO_LSTM_TC");
+  const bool rec_tc = P->use_tc && !(no_rec && no_rec[0] == '1');
+  const int r = lstm_tc_create(*d, rec_tc, P->base + P->bytes, workspace_bytes - P->bytes, &P->lstm_tc);
   if (r != LAGVAE_OK) {
     delete P;
     return r;
