@@ -1,0 +1,113 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of lagvae.dp.dp_inner_step with an oracle back-end must equal
+the single-process step on the full batch (exact reference semantics under batch sharding)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _setup_path():
+    for p in (os.path.join(ROOT, "vae-lagging-encoder_b200"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+class OracleBackend:
+    """CPU stand-in for EngineBackend: gradients from the oracle (test-only)."""
+
+    def __init__(self, eps_global, klw, lo):
+        self.eps, self.klw, self.lo = eps_global, klw, lo
+
+    def forward_backward(self, params, x, g_scale, flat):
+        import lagging_oracle as O
+        leaves = {k: p.detach().clone().requires_grad_(True) for k, p in zip(O.ALL_KEYS, params)}
+        eps = self.eps[self.lo:self.lo + x.shape[0]]
+        loss, _, _ = O.vae_loss(leaves, x, self.klw, eps)
+        (loss * g_scale).sum().backward()
+        off = 0
+        for k in O.ALL_KEYS:
+            g = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
+            if k == "decoder.embed.weight":
+                g[-1].zero_()
+            flat[off:off + g.numel()] = g.reshape(-1)
+            off += g.numel()
+        return loss.detach()
+
+    def clip_sgd(self, params, flat, max_norm, lr):
+        import lagging_oracle as O
+        norm = float(flat.double().norm())
+        coef = O.clip_coef(norm, max_norm)
+        off = 0
+        for i, p in enumerate(params):
+            n = p.numel()
+            if i < 6:
+                p -= lr * coef * flat[off:off + n].view_as(p)
+            off += n
+        return norm
+
+
+def _worker(rank, world, port, B, out_q):
+    _setup_path()
+    import lagging_oracle as O
+    from lagvae.dp import dp_inner_step, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, ni, nh, nz, T = 60, 6, 8, 2, 5
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=4))
+    params = [p[k] for k in O.ALL_KEYS]
+    x = O.make_token_batch(B, T, V)
+    eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
+    flat = torch.zeros(sum(q.numel() for q in params))
+    lo, hi = shard_bounds(B, rank, world)
+    loss_sum, norm = dp_inner_step(OracleBackend(eps, 0.5, lo), params, x, flat, max_norm=0.05)
+    out_q.put((rank, loss_sum, norm, [q.clone() for q in params[:6]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [6, 5, 1])   # even, ragged, and an empty shard on rank 1
+def test_two_rank_gloo_equals_single_process(B):
+    _setup_path()
+    import lagging_oracle as O
+    world, port = 2, 29000 + os.getpid() % 2000 + B
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    # single-process reference on the full batch
+    V, ni, nh, nz, T = 60, 6, 8, 2, 5
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=4))
+    x = O.make_token_batch(B, T, V)
+    eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
+    r = O.inner_step(p, x, 0.5, eps, max_norm=0.05, update=True)
+    for rank, loss_sum, norm, enc in res:
+        assert abs(loss_sum - r["loss_sum"]) <= 1e-5 * abs(r["loss_sum"])
+        assert abs(norm - r["grad_norm"]) <= 1e-5 * r["grad_norm"]
+        assert r["coef"] < 1.0          # the clip is active: the norm of the AVERAGED gradient matters
+        for k, got in zip(O.ENC_KEYS, enc):
+            assert float((got - p[k]).abs().max()) <= 1e-6 * max(1.0, float(p[k].abs().max())), k
+    # replicas stay bit-identical without a parameter broadcast
+    for a, b in zip(res[0][3], res[1][3]):
+        assert torch.equal(a, b)
+
+
+def test_shard_bounds_cover_and_partition():
+    _setup_path()
+    from lagvae.dp import shard_bounds
+    for n in (0, 1, 5, 32, 33):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
