@@ -214,17 +214,18 @@ def run_ours(args, rank, world, local_rank):
         seed_ctr[0] += 1
         return lagvae.DropoutSpec(2, 0.5, 0.5, None, None, 783435 * 1000003 + seed_ctr[0] * 7919 + rank)
 
+    from lagvae.dp import EngineBackend, dp_inner_step
+    backend = EngineBackend(eng, KL_WEIGHT, lambda b: torch.empty(b, 1, c["nz"], device=dev).normal_(generator=gen), drop)
+
     def step_fused(i):
         x = pool[picks[i]]
-        eps = torch.empty(B, 1, c["nz"], device=dev).normal_(generator=gen)       # encoder.py:77
+        eps = torch.empty(B, 1, c["nz"], device=dev).normal_(generator=gen) if world == 1 else None   # encoder.py:77
         if world == 1:
             eng.inner_step(params, x, eps, KL_WEIGHT, drop(), gw, out_loss, sc)   # text.py:373-387 fused
         else:
-            loss, _, _ = eng.loss_forward(params, x, eps, KL_WEIGHT, drop())
-            gl = torch.full((B,), 1.0 / (B * world), device=dev)                   # mean over the GLOBAL batch
-            eng.loss_backward(params, x, gl, None, None, grads_out=grads)
-            dist.all_reduce(gw)                                                    # ONE all-reduce per inner step
-            eng.clip_sgd(params, grads, 6, 5.0, 1.0, scale_all=False)
+            # tested host logic (tests/test_dp_gloo.py): shard-local fwd+bwd with 1/(B*N) upstream gradient,
+            # ONE all-reduce of the flat gradient, clip + SGD on the averaged gradient
+            dp_inner_step(backend, params, x, gw, presharded=True, global_rows=B * world)
 
     def barrier():
         if world > 1:
@@ -257,7 +258,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- e2e: drop-in modules API, host token ids, per-step readback ----------------
     e2e = None
-    if True:
+    if not args.no_e2e:
         import types
         import modules
 
@@ -359,6 +360,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the CPU / torch-GPU side baselines")
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the module-API leg (profiling runs only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

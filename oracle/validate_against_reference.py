@@ -210,7 +210,7 @@ def main():
         loss, rec, kl = vae.loss(x, 0.1)
         vae.zero_grad()
         loss.mean(dim=-1).backward()
-        grads = {k: q.grad for k, q in zip(O.ALL_KEYS, vae.parameters())}
+        grads = {k: (q.grad.clone() if q.grad is not None else None) for k, q in zip(O.ALL_KEYS, vae.parameters())}  # clone: clip scales .grad in place
         gn = float(torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0))
         torch.manual_seed(1)
         eps = torch.zeros(B, 1, nz).normal_()

@@ -238,13 +238,17 @@ def test_yahoo_shape_against_reference_fingerprints(golden, force_simt):
     assert_close(kl, g["kl"], OUT_TOL, "kl", floor=1e-2)
     assert_close(mu, g["mu"], OUT_TOL, "mu", floor=1e-2)
     grads = eng.loss_backward(params, x, torch.full((B,), 1.0 / B, device="cuda"), None, None)
-    tot = 0.0
+    tot, bad = 0.0, []
     for k, gr in zip(O.ALL_KEYS, grads):
         n = float(gr.double().norm())
         tot += n * n
-        assert abs(n - float(g["gnorm." + k])) <= 2e-3 * max(float(g["gnorm." + k]), 1e-6), k
-        sl = gr.reshape(-1)[:: max(1, gr.numel() // 64)][:64].cpu()
-        assert_close(sl, g["gslice." + k], 5e-3, "grad slice " + k, floor=float(gr.abs().max()) * 0.05)
+        want = float(g["gnorm." + k])
+        sl = gr.reshape(-1)[:: max(1, gr.numel() // 64)][:64].cpu().double()
+        ws = torch.from_numpy(g["gslice." + k]).double()
+        serr = float((sl - ws).abs().max()) / max(float(gr.abs().max()) * 0.05, float(ws.abs().max()), 1e-12)
+        if abs(n - want) > 2e-3 * max(want, 1e-6) or serr > 5e-3:
+            bad.append("%s: norm %.6g want %.6g, slice err %.2e" % (k, n, want, serr))
+    assert not bad, "\n".join(bad)
     assert abs(tot ** 0.5 - float(g["grad_norm"])) <= 1e-3 * float(g["grad_norm"])
     m2, l2 = eng.encode_stats(params, x)
     mi = float(eng.mi(m2, l2, torch.from_numpy(g["eps_mi"]).cuda()))

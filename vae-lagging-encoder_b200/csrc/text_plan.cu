@@ -248,10 +248,12 @@ int lstm_backward_steps(const float* w_hh, const float* c0, const float* gates, 
   const int64_t gs = (int64_t)Bd * 4 * nh, hs = (int64_t)Bd * nh;
   LV_TRY(fill(dc, 0.f, hs, st));
   for (int t = Tn - 1; t >= 0; --t) {
+    // dh_last (gradient on the final h only) adds to dh_ext at t = Tn-1; it rides in the dh_rec slot there
     const float* ext = dh_ext ? dh_ext + t * hs : (t == Tn - 1 ? dh_last : nullptr);
     const DropSpec ds = dh_ext ? drop : spec_none();
     const float* cp = t ? c_all + (t - 1) * hs : c0;
-    LV_TRY(lstm_point_bwd(gates + t * gs, c_all + t * hs, cp, ext, ds, t == Tn - 1 ? nullptr : dh_rec, dc,
+    const float* rec = t == Tn - 1 ? (dh_ext ? dh_last : nullptr) : dh_rec;
+    LV_TRY(lstm_point_bwd(gates + t * gs, c_all + t * hs, cp, ext, ds, rec, dc,
                           dgates + t * gs, t, Tn, Bd, nh, st));
     if (t > 0 || want_init)  // dh_{t-1} = dG_t · W_hh
       LV_TRY(gemm_f32(dgates + t * gs, 4 * nh, 1, w_hh, 1, nh, dh_rec, nh, Bd, nh, 4 * nh, 1.f, 0.f, nullptr,
