@@ -125,7 +125,7 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* plan, const lagvae_text_para
  * the gradient tensors; params/grads pair up by index.  out_norm (device fp32[1]) receives the
  * pre-clip total L2 norm.  scale_all_grads != 0 also multiplies every gradient by the clip
  * coefficient in place (what clip_grad_norm_ does); 0 skips that write for tensors that are not
- * updated (their clipped value is dead in the aggressive loop). scratch: device, >= 4 KiB. */
+ * updated (their clipped value is dead in the aggressive loop). scratch: device, >= 16 KiB. */
 int lagvae_clip_sgd_step(float* const* h_params, float* const* h_grads, const int64_t* h_counts,
                          int n_seg, int n_update, float max_norm, float lr, int scale_all_grads,
                          float* out_norm, void* scratch, void* stream);

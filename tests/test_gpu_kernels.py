@@ -161,7 +161,7 @@ def test_clip_sgd_matches_torch():
         G = (C.c_void_p * n)(*[g.data_ptr() for g in gs])
         cnt = (C.c_int64 * n)(*[g.numel() for g in gs])
         norm = torch.empty(1, device="cuda")
-        scratch = torch.empty(4096, dtype=torch.uint8, device="cuda")
+        scratch = torch.empty(16384, dtype=torch.uint8, device="cuda")
         be.check(be.lib().lagvae_clip_sgd_step(P, G, cnt, n, 2, 5.0, 1.0, 1, be.ptr(norm), be.ptr(scratch), _st()))
         assert abs(float(norm) - float(norm_ref)) < 1e-5 * float(norm_ref)
         for p, rp, g in zip(ps, ref_p, gs):

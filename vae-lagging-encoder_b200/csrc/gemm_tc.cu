@@ -69,7 +69,9 @@ constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;            // 16 KiB per operand part
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi A_lo B_hi B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int CSTRIDE = 36;                        // floats per staged row (32 + 4 pad: conflict-free float4 both ways)
+constexpr int CSTAGE_BYTES = 4 * 32 * CSTRIDE * 4; // epilogue staging: 4 warps x 32 rows
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CSTAGE_BYTES;
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 256;
 
@@ -215,60 +217,78 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     __syncwarp();
   } else {
     // ================================ epilogue ================================
+    // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose -> row-contiguous global stores:
+    // every store instruction of a warp covers 4 rows x 128 B (vector path) or 1 row x 128 B (unaligned C).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    float* cst = (float*)(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (warp - 2) * 32 * CSTRIDE;
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((((uintptr_t)g.bias_n) & 15) == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mb = tile % m_blks, nb = tile / m_blks;
-      const int row = mb * BM + quad * 32 + lane;
+      const int row0 = mb * BM + quad * 32;
       const int n0 = nb * BN;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const bool row_ok = row < g.M;
-      const int64_t orow = row_ok ? (g.row_map ? (int64_t)g.row_map[row] : (int64_t)row) : 0;
-      float* crow = g.C + orow * g.ldc;
-      const float* brow = (g.bias_rows && row_ok) ? g.bias_rows + (int64_t)(row % g.bias_period) * g.N : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         ptx::tmem_ld_wait();
-        if (row_ok) {
-          const int cb = n0 + c * 32;
-          const bool vec = (cb + 32 <= g.N) && ((((uintptr_t)(crow + cb)) & 15) == 0);
-          if (vec) {
+        float* mine = cst + lane * CSTRIDE;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
+        for (int j = 0; j < 32; j += 4)
+          *(float4*)(mine + j) = make_float4(g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
+                                             g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int cb = n0 + c * 32;
+        if (vec_ok) {
+          const int cc = (lane & 7) * 4, col = cb + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), row = row0 + rr;
+            if (row < g.M && col < g.N) {
+              float4 v = *(const float4*)(cst + rr * CSTRIDE + cc);
               float* vp = &v.x;
+              const int64_t orow = g.row_map ? (int64_t)g.row_map[row] : (int64_t)row;
+              float* dst = g.C + orow * g.ldc + col;
+              const float* brow = g.bias_rows ? g.bias_rows + (int64_t)(row % g.bias_period) * g.N : nullptr;
+              if (col + 3 < g.N) {
+                if (g.bias_n) { const float4 b = *(const float4*)(g.bias_n + col); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+                if (brow) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float x = g.alpha * __uint_as_float(r[j + q]);
-                if (g.bias_n) x += g.bias_n[cb + j + q];
-                if (brow) x += brow[cb + j + q];
-                vp[q] = x;
-              }
-              float4* dst = (float4*)(crow + cb + j);
-              if (g.beta != 0.f) {
-                const float4 o = *dst;
-                v.x += g.beta * o.x; v.y += g.beta * o.y; v.z += g.beta * o.z; v.w += g.beta * o.w;
-              }
-              *dst = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = cb + j;
-              if (col < g.N) {
-                float x = g.alpha * __uint_as_float(r[j]);
-                if (g.bias_n) x += g.bias_n[col];
-                if (brow) x += brow[col];
-                if (g.beta != 0.f) x += g.beta * crow[col];
-                crow[col] = x;
+                  for (int q = 0; q < 4; ++q) vp[q] += brow[col + q];
+                }
+                if (g.beta != 0.f) { const float4 o = *(const float4*)dst; v.x += g.beta * o.x; v.y += g.beta * o.y; v.z += g.beta * o.z; v.w += g.beta * o.w; }
+                *(float4*)dst = v;
+              } else {
+                for (int q = 0; q < 4 && col + q < g.N; ++q) {
+                  float x = vp[q];
+                  if (g.bias_n) x += g.bias_n[col + q];
+                  if (brow) x += brow[col + q];
+                  if (g.beta != 0.f) x += g.beta * dst[q];
+                  dst[q] = x;
+                }
               }
             }
           }
+        } else {
+          const int col = cb + lane;
+          if (col < g.N) {
+            const float bn = g.bias_n ? g.bias_n[col] : 0.f;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = row0 + rr;
+              if (row >= g.M) break;
+              float x = cst[rr * CSTRIDE + lane] + bn;
+              if (g.bias_rows) x += g.bias_rows[(int64_t)(row % g.bias_period) * g.N + col];
+              const int64_t orow = g.row_map ? (int64_t)g.row_map[row] : (int64_t)row;
+              float* dst = g.C + orow * g.ldc + col;
+              if (g.beta != 0.f) x += g.beta * (*dst);
+              *dst = x;
+            }
+          }
         }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();

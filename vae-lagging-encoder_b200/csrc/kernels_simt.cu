@@ -27,11 +27,14 @@ const char* last_error() { return g_err; }
 // ---------------------------------------------------------------------------------------------
 constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
 
+// SPLITK: blockIdx.z owns K range [z*kchunk, (z+1)*kchunk) and atomically adds alpha*partial into C
+// (C pre-initialised to beta*C + bias by k_gemm_prep) — for skinny outputs with a long contraction.
+template <bool SPLITK>
 __global__ void __launch_bounds__(256)
 k_gemm_f32(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
            int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc, int M, int N, int K,
            float alpha, float beta, const float* __restrict__ bias_n,
-           const float* __restrict__ bias_rows, int bias_period) {
+           const float* __restrict__ bias_rows, int bias_period, int kchunk) {
   __shared__ float As[GB_K][GB_M + 4];
   __shared__ float Bs[GB_K][GB_N + 4];
   const int tid = threadIdx.x;
@@ -45,18 +48,20 @@ k_gemm_f32(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float*
 
   // loader mapping: pick the thread->element order that walks the contiguous dimension
   const bool a_kfast = (a_cs == 1), b_kfast = (b_cs == 1);
-  for (int k0 = 0; k0 < K; k0 += GB_K) {
+  const int kbeg = SPLITK ? blockIdx.z * kchunk : 0;
+  const int kend = SPLITK ? min(K, kbeg + kchunk) : K;
+  for (int k0 = kbeg; k0 < kend; k0 += GB_K) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int e = tid + r * 256;  // 0..1023 = 64 x 16
       int mm, kk;
       if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[(int64_t)gm * a_rs + (int64_t)gk * a_cs] : 0.f;
+      As[kk][mm] = (gm < M && gk < kend) ? A[(int64_t)gm * a_rs + (int64_t)gk * a_cs] : 0.f;
       int nn, kb;
       if (b_kfast) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
       const int gn = n0 + nn, gkb = k0 + kb;
-      Bs[kb][nn] = (gn < N && gkb < K) ? B[(int64_t)gn * b_rs + (int64_t)gkb * b_cs] : 0.f;
+      Bs[kb][nn] = (gn < N && gkb < kend) ? B[(int64_t)gn * b_rs + (int64_t)gkb * b_cs] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -82,13 +87,29 @@ k_gemm_f32(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float*
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
-      if (bias_n) v += bias_n[gn];
-      if (bias_rows) v += bias_rows[(int64_t)(gm % bias_period) * N + gn];
       float* c = C + (int64_t)gm * ldc + gn;
-      if (beta != 0.f) v += beta * (*c);
-      *c = v;
+      if (SPLITK) {
+        atomicAdd(c, v);
+      } else {
+        if (bias_n) v += bias_n[gn];
+        if (bias_rows) v += bias_rows[(int64_t)(gm % bias_period) * N + gn];
+        if (beta != 0.f) v += beta * (*c);
+        *c = v;
+      }
     }
   }
+}
+
+__global__ void k_gemm_prep(float* __restrict__ C, int64_t ldc, int M, int N, float beta,
+                            const float* __restrict__ bias_n, const float* __restrict__ bias_rows, int bias_period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  float* c = C + (int64_t)m * ldc + n;
+  float v = beta != 0.f ? beta * (*c) : 0.f;
+  if (bias_n) v += bias_n[n];
+  if (bias_rows) v += bias_rows[(int64_t)(m % bias_period) * N + n];
+  *c = v;
 }
 
 int gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
@@ -98,8 +119,18 @@ int gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t
   LV_CHECK_ARG(K >= 0 && (bias_rows == nullptr || bias_period > 0), "gemm_f32: bad K/bias_period");
   dim3 grid((unsigned)cdiv(N, GB_N), (unsigned)cdiv(M, GB_M));
   LV_CHECK_ARG(grid.y <= 65535, "gemm_f32: M too large (%d)", M);
-  k_gemm_f32<<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, alpha, beta, bias_n,
-                                    bias_rows, bias_period);
+  if ((int64_t)grid.x * grid.y <= 16 && K >= 512) {   // skinny output, long contraction: split K over the grid
+    const int kchunk = 128;
+    grid.z = (unsigned)cdiv(K, kchunk);
+    k_gemm_prep<<<(int)cdiv((int64_t)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta, bias_n, bias_rows, bias_period);
+    LV_LAUNCH_CHECK();
+    k_gemm_f32<true><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, alpha, beta, bias_n,
+                                            bias_rows, bias_period, kchunk);
+    LV_LAUNCH_CHECK();
+    return LAGVAE_OK;
+  }
+  k_gemm_f32<false><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, alpha, beta, bias_n,
+                                           bias_rows, bias_period, 0);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }
@@ -401,20 +432,36 @@ int col_sum(const float* src, int rows, int ncol, float* out1, float* out2, cuda
 // cross entropy over materialised logits — dec_lstm.py:47,143-148 (CrossEntropyLoss(weight=1,
 // reduce=False) then sum over time).  One block per (t,bd) row.
 // ---------------------------------------------------------------------------------------------
+// online (single-pass) log-sum-exp: each thread keeps a running (max, sum), merged warp- then block-wide
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float nm = fmaxf(m, m2);
+  const float a = (m == -INFINITY) ? 0.f : s * expf(m - nm);
+  const float b = (m2 == -INFINITY) ? 0.f : s2 * expf(m2 - nm);
+  m = nm;
+  s = a + b;
+}
 __global__ void __launch_bounds__(256)
 k_ce_fwd(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ x,
          int64_t x_ld, int Bd, int ns, float* __restrict__ lse_out, float* __restrict__ loss_row) {
-  __shared__ float red[32];
+  __shared__ float red_m[8], red_s[8];
   const int row = blockIdx.x;
   const int bd = row % Bd, t = row / Bd;
   const float* l = logits + (int64_t)row * ld;
-  float m = -INFINITY;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, l[v]);
-  m = block_max(m, red);
-  float s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(l[v] - m);
-  s = block_sum(s, red);
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float xv = l[v];
+    if (xv > m) { s = s * expf(m - xv) + 1.f; m = xv; } else { s += expf(xv - m); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(m, s, m2, s2);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red_m[w] = m; red_s[w] = s; }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) lse_merge(m, s, red_m[i], red_s[i]);
     const float lse = m + logf(s);
     const int64_t tgt = x[(int64_t)(bd / ns) * x_ld + 1 + t];  // tgt = x[:,1:]  dec_lstm.py:127
     lse_out[row] = lse;
@@ -446,6 +493,41 @@ k_ce_bwd(float* __restrict__ logits, int64_t ld, int V, const int64_t* __restric
 int ce_bwd(float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd, int ns,
            const float* lse, const float* g_rec, cudaStream_t st) {
   k_ce_bwd<<<Tn * Bd, 256, 0, st>>>(logits, ld, V, x, x_ld, Bd, ns, lse, g_rec);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
+
+// same, but emits dlogits directly as the split-bf16 (hi, lo) GEMM operand [rows, ld_out] (pad columns = 0):
+// saves the fp32 write + re-read of the 509 MB tensor
+__global__ void __launch_bounds__(256)
+k_ce_bwd_split(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ x, int64_t x_ld,
+               int Bd, int ns, const float* __restrict__ lse, const float* __restrict__ g_rec,
+               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  const int row = blockIdx.x;
+  const int bd = row % Bd, t = row / Bd, b = bd / ns;
+  const float g = g_rec[b] / (float)ns;
+  const float L = lse[row];
+  const int64_t tgt = x[(int64_t)b * x_ld + 1 + t];
+  const float* l = logits + (int64_t)row * ld;
+  __nv_bfloat16* h = hi + (int64_t)row * ld_out;
+  __nv_bfloat16* w = lo + (int64_t)row * ld_out;
+  for (int v = threadIdx.x; v < (int)ld_out; v += blockDim.x) {
+    float d = 0.f;
+    if (v < V) {
+      float p = expf(l[v] - L);
+      if (v == tgt) p -= 1.f;
+      d = p * g;
+    }
+    __nv_bfloat16 a, c;
+    split_bf16(d, a, c);
+    h[v] = a;
+    w[v] = c;
+  }
+}
+int ce_bwd_split(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd, int ns,
+                 const float* lse, const float* g_rec, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st) {
+  k_ce_bwd_split<<<Tn * Bd, 256, 0, st>>>(logits, ld, V, x, x_ld, Bd, ns, lse, g_rec, (__nv_bfloat16*)hi,
+                                           (__nv_bfloat16*)lo, ld_out);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }
@@ -520,17 +602,30 @@ struct SegTable {
   int64_t n[16];
   int nseg, nupd;
 };
-// partial Σg² per block into scratch[blockIdx.x] (double), deterministic two-stage reduce
+// partial Σg² per block into scratch[blockIdx.x] (double), deterministic two-stage reduce.  Per-thread
+// accumulation is fp32 in 4 independent lanes over <= ~1 K elements (B200 fp64 rate is far too low to use it
+// in the streaming loop); the cross-thread / cross-block reduction is fp64.
 __global__ void __launch_bounds__(256) k_sumsq(SegTable tb, double* __restrict__ partial) {
   __shared__ double red[256];
   double a = 0.0;
   for (int s = 0; s < tb.nseg; ++s) {
     const float* g = tb.g[s];
     const int64_t n = tb.n[s];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const float v = g[i];
-      a += (double)v * v;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    if ((((uintptr_t)g) & 15) == 0) {
+      const int64_t n4 = n >> 2;
+      const float4* g4 = (const float4*)g;
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        p0 = fmaf(v.x, v.x, p0); p1 = fmaf(v.y, v.y, p1); p2 = fmaf(v.z, v.z, p2); p3 = fmaf(v.w, v.w, p3);
+      }
+      for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p0 = fmaf(g[i], g[i], p0);
+    } else {
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p0 = fmaf(g[i], g[i], p0);
     }
+    a += (double)p0 + (double)p1 + (double)p2 + (double)p3;
   }
   red[threadIdx.x] = a;
   __syncthreads();
@@ -586,9 +681,9 @@ int clip_sgd_step(float* const* h_params, float* const* h_grads, const int64_t* 
     tb.g[i] = h_grads[i];
     tb.n[i] = h_counts[i];
   }
-  const int nblk = 148 * 2;  // 296 partials * 8 B = 2368 B of scratch, coef at +3072
+  const int nblk = 148 * 8;  // 1184 partials * 8 B = 9472 B of scratch, coef at +12288
   double* partial = (double*)scratch;
-  float* coef = (float*)((char*)scratch + 3072);
+  float* coef = (float*)((char*)scratch + 12288);
   k_sumsq<<<nblk, 256, 0, st>>>(tb, partial);
   LV_LAUNCH_CHECK();
   k_norm_finish<<<1, 256, 0, st>>>(partial, nblk, max_norm, out_norm, coef);

@@ -28,8 +28,7 @@ constexpr int NTHREADS = 288;             // warps 0-3 epilogue, warp 4 MMA issu
 constexpr int NPROD = 128;
 constexpr int A_PART = 64 * 128;          // 8 KiB: 64 rows x 128 B (64 bf16 of K)
 constexpr int STAGE_BYTES = 2 * A_PART;   // hi + lo
-constexpr int LAG = 4;                    // cp.async groups in flight behind the newest one
-constexpr int MAX_MT = 8;                 // m-tiles of 64 batch rows (Bd <= 512)
+constexpr int MAX_MT = 4;                 // m-tiles of 64 batch rows (Bd <= 256; 4 accumulator slots x 32 cols each)
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB
 
 struct RecArgs {
@@ -110,32 +109,26 @@ __device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, 
   const int rows = min(64, a.Bd - mt * 64);
   const int per_part = rows * 8;
   const int64_t part_stride = (int64_t)a.Bd * a.KP;
-  int sig_stage = ps.stage;  // stage of the oldest un-signalled group
-  for (int kb = 0; kb < a.KB + LAG; ++kb) {
-    if (kb < a.KB) {
-      ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
-      const uint32_t sbase = sm.a_base + ps.stage * STAGE_BYTES;
-      for (int id = ptid; id < 2 * per_part; id += NPROD) {
-        const int part = id >= per_part;
-        const int rem = id - part * per_part;
-        const int r = rem >> 3, c = rem & 7;
-        const __nv_bfloat16* src = slot + part * part_stride + (int64_t)(mt * 64 + r) * a.KP + kb * 64 + c * 8;
-        ptx::cp_async_cg16(sbase + part * A_PART + sw128(r, c), src);
-      }
-      if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+  for (int kb = 0; kb < a.KB; ++kb) {
+    ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
+    const uint32_t sbase = sm.a_base + ps.stage * STAGE_BYTES;
+    for (int id = ptid; id < 2 * per_part; id += NPROD) {
+      const int part = id >= per_part;
+      const int rem = id - part * per_part;
+      const int r = rem >> 3, c = rem & 7;
+      const __nv_bfloat16* src = slot + part * part_stride + (int64_t)(mt * 64 + r) * a.KP + kb * 64 + c * 8;
+      ptx::cp_async_cg16(sbase + part * A_PART + sw128(r, c), src);
     }
-    ptx::cp_async_commit();
-    if (kb >= LAG) {  // group kb-LAG has landed for this thread
-      ptx::cp_async_wait<LAG>();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(sm.full(sig_stage));
-      if (++sig_stage == a.NS) sig_stage = 0;
-    }
+    // asynchronous arrive: fires when this thread's copies above have landed (no blocking wait, so every
+    // ring stage is in flight at once); the consumer issues the generic->async proxy fence after its wait
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sm.full(ps.stage)) : "memory");
+    if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
   }
-  ptx::cp_async_wait<0>();
 }
 
 // ---- MMA issuer: one K sweep for m-tile mt ------------------------------------------------------
+constexpr int NACC = 4;  // independent TMEM accumulators per m-tile (one per K sub-step): no dependent-accumulate chain
+
 template <int NB>
 __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeState& ps, uint32_t d_tmem,
                                          uint32_t acc_bar) {
@@ -143,6 +136,7 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
   constexpr int WT = NB * 128;  // bytes of one weight tile (NB rows x 128 B)
   for (int kb = 0; kb < a.KB; ++kb) {
     ptx::mbar_wait(sm.full(ps.stage), ps.phase);
+    ptx::fence_proxy_async_smem();   // cp.async (generic proxy) writes -> visible to the UMMA (async proxy) reads
     ptx::tc_fence_after();
     const uint32_t sa = sm.a_base + ps.stage * STAGE_BYTES;
     const uint32_t sw = sm.w_base + (uint32_t)(kb * 2) * WT;
@@ -152,9 +146,10 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
       const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + A_PART + k * 32, 16, 1024);
       const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
       const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
-      ptx::umma_f16(d_tmem, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
-      ptx::umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-      ptx::umma_f16(d_tmem, a_lo, b_hi, idesc, 1u);
+      const uint32_t d = d_tmem + (uint32_t)(k * NB);
+      ptx::umma_f16(d, a_hi, b_hi, idesc, kb ? 1u : 0u);
+      ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+      ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
     }
     ptx::umma_commit(sm.empty(ps.stage, a.NS));
     if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
@@ -204,7 +199,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, u0 = blockIdx.x * 8;
-  const int tmem_cols = a.m_tiles * 32 <= 32 ? 32 : (a.m_tiles * 32 <= 64 ? 64 : (a.m_tiles * 32 <= 128 ? 128 : 256));
+  const int need_cols = a.m_tiles * 32 * NACC;
+  const int tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
 
   // resident W_hh slice: tile (kb, part) = [32 rows x 64 k] bf16, rows n = gate*8 + uu
   for (int id = threadIdx.x; id < 32 * (a.KP / 8); id += NTHREADS) {
@@ -242,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
     } else if (warp == 4) {
       if (lane == 0)
         for (int mt = 0; mt < a.m_tiles; ++mt)
-          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32), sm.acc(mt, a.NS));
+          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32 * NACC), sm.acc(mt, a.NS));
       __syncwarp();
     } else {
       float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
@@ -264,17 +260,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
         }
         ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)(t & 1));
         ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 32), r);
-        ptx::tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < NACC; ++sl) {   // sum the independent accumulator slots
+          uint32_t r[32];
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 32 * NACC + sl * 32), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        }
         if (valid) {
           float hv[8], cv[8], act[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float ig = sigmoidf_(pre[j] + __uint_as_float(r[j]));
-            const float fg = sigmoidf_(pre[8 + j] + __uint_as_float(r[8 + j]));
-            const float gg = tanhf(pre[16 + j] + __uint_as_float(r[16 + j]));
-            const float og = sigmoidf_(pre[24 + j] + __uint_as_float(r[24 + j]));
+            const float ig = sigmoidf_(pre[j] + acc[j]);
+            const float fg = sigmoidf_(pre[8 + j] + acc[8 + j]);
+            const float gg = tanhf(pre[16 + j] + acc[16 + j]);
+            const float og = sigmoidf_(pre[24 + j] + acc[24 + j]);
             const float c = fg * cp[j] + ig * gg;
             cv[j] = c;
             hv[j] = og * tanhf(c);
@@ -323,7 +327,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, Tn = a.Tn, u0 = blockIdx.x * 8;
-  const int tmem_cols = a.m_tiles * 8 <= 32 ? 32 : 64;
+  const int need_cols = a.m_tiles * 8 * NACC;
+  const int tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : 256));
 
   // resident W_hhᵀ slice: rows n = unit uu, K index = gate column k in [0, 4nh): W_hh[k, u0+uu]
   for (int id = threadIdx.x; id < 8 * (a.KP / 8); id += NTHREADS) {
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
     } else if (warp == 4) {
       if (has_rec && lane == 0)
         for (int mt = 0; mt < a.m_tiles; ++mt)
-          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8), sm.acc(mt, a.NS));
+          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8 * NACC), sm.acc(mt, a.NS));
       __syncwarp();
     } else {
       for (int mt = 0; mt < a.m_tiles; ++mt) {
@@ -384,25 +389,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
             dhx[j] = e;
           }
         }
-        uint32_t r[8];
+        float rec[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = 0u;
+        for (int j = 0; j < 8; ++j) rec[j] = 0.f;
         if (has_rec) {
           ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)((s - 1) & 1));
           ptx::tc_fence_after();
-          tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 8), r);
-          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int sl = 0; sl < NACC; ++sl) {
+            uint32_t r[8];
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 8 * NACC + sl * 8), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rec[j] += __uint_as_float(r[j]);
+          }
         }
         if (valid) {
           if (t < 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a.dh_rec_out[(int64_t)b * nh + u0 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 8; ++j) a.dh_rec_out[(int64_t)b * nh + u0 + j] = rec[j];
           } else {
             float dg[32], dcn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float ig = gt[j], fg = gt[8 + j], gg = gt[16 + j], og = gt[24 + j];
-              const float dh = __uint_as_float(r[j]) + dhx[j];
+              const float dh = rec[j] + dhx[j];
               const float tc = tanhf(cc[j]);
               const float dct = dcv[j] + dh * og * (1.f - tc * tc);
               dg[j] = dct * gg * ig * (1.f - ig);
@@ -461,7 +472,7 @@ static bool shape_supported(const lagvae_text_dims& d, int* nsf, int* nsb, size_
   const int64_t misc = 1024 + 8 * (2 * 8 + MAX_MT) + 64;
   const int nf = (int)std::min<int64_t>(8, (SMEM_LIMIT - wf - misc) / STAGE_BYTES);
   const int nb = (int)std::min<int64_t>(8, (SMEM_LIMIT - wb - misc) / STAGE_BYTES);
-  if (nf < LAG + 1 || nb < LAG + 1) return false;
+  if (nf < 2 || nb < 2) return false;
   *nsf = nf;
   *nsb = nb;
   *smf = (size_t)(wf + (int64_t)nf * STAGE_BYTES + misc);

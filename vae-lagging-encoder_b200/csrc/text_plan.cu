@@ -29,6 +29,7 @@ struct lagvae_text_plan {
   bool use_tc;
   int Bd, Te, Td;
   int64_t re, rd;
+  int64_t ldl;  // leading dimension of the logits buffer (V padded to 8: 16-B aligned rows)
   char* base;
   size_t bytes;
   // forward stash
@@ -46,6 +47,7 @@ struct lagvae_text_plan {
   lagvae_dropout drop;
   float kl_weight;
   bool have_forward;
+  int dec_wgrad_passes;  // 3 = fp32-grade; 1 = single bf16 pass (fused inner step: these gradients only feed the clip norm)
 };
 
 namespace {
@@ -100,7 +102,8 @@ void carve(lagvae_text_plan* P, char* base) {
   P->c_d = c.take<float>(rd * nh);
   P->h_d = c.take<float>(rd * nh);
   P->hdrop_d = c.take<float>(rd * nh);
-  P->logits = c.take<float>(rd * V);
+  P->ldl = round_up(V, 8);
+  P->logits = c.take<float>(rd * P->ldl);
   P->lse = c.take<float>(rd);
   P->loss_row = c.take<float>(rd);
   P->scalars = c.take<float>(8);
@@ -120,7 +123,7 @@ void carve(lagvae_text_plan* P, char* base) {
   P->dx_e = c.take<float>(re * ni);
   P->dc_e = c.take<float>(B * nh);
   P->dh_rec_e = c.take<float>(B * nh);
-  P->clip_scratch = c.take<char>(4096);
+  P->clip_scratch = c.take<char>(16384);
   P->arena_bytes = P->use_tc ? arena_need(d) : 0;
   P->arena = c.take<char>((int64_t)P->arena_bytes);
   c.off = (size_t)round_up((int64_t)c.off, 256);
@@ -156,6 +159,27 @@ Staged stage(lagvae_text_plan* P, Mat m, cudaStream_t st, int* status) {
   P->arena_off = off + need;
   const int r = split_bf16_launch(m.p, m.ld, (int)m.rows, (int)m.cols, hi, lo, ldo, st);
   if (r != LAGVAE_OK) *status = r;
+  s.tc = TcOperand{hi, lo, ldo, 0};
+  return s;
+}
+
+// arena allocation only (the producer kernel writes the hi/lo parts itself); fp32 view is absent
+Staged stage_alloc(lagvae_text_plan* P, int64_t rows, int64_t cols, int* status) {
+  Staged s;
+  s.m = Mat{nullptr, rows, cols, cols};
+  s.tc = TcOperand{nullptr, nullptr, 0, 0};
+  const int64_t ldo = round_up(cols, 8);
+  const size_t need = (size_t)rows * ldo * sizeof(uint16_t);
+  size_t off = (size_t)round_up((int64_t)P->arena_off, 256);
+  if (off + 2 * need + 512 > P->arena_bytes) {
+    set_error("text plan: tensor-core staging arena exhausted");
+    *status = LAGVAE_E_WORKSPACE;
+    return s;
+  }
+  uint16_t* hi = (uint16_t*)(P->arena + off);
+  off = (size_t)round_up((int64_t)(off + need), 256);
+  uint16_t* lo = (uint16_t*)(P->arena + off);
+  P->arena_off = off + need;
   s.tc = TcOperand{hi, lo, ldo, 0};
   return s;
 }
@@ -315,8 +339,8 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   Staged sh = stage(P, Mat{hdrop ? hdrop : P->h_d, P->rd, nh, nh}, st, &status);
   Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
   LV_TRY(status);
-  LV_TRY(mm(P, sh, false, swp, false, P->logits, V, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
-  LV_TRY(ce_fwd(P->logits, V, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
+  LV_TRY(mm(P, sh, false, swp, false, P->logits, P->ldl, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
   return LAGVAE_OK;
 }
 
@@ -399,6 +423,7 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
     return r;
   }
   P->have_forward = false;
+  P->dec_wgrad_passes = 3;
   *out = P;
   return LAGVAE_OK;
 }
@@ -490,17 +515,28 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   LV_TRY(combine_upstream(g_loss, g_rec, g_kl, P->kl_weight, B, P->g_rec, P->g_kl, st));
 
   // ---- CE + vocabulary projection backward (autograd of dec_lstm.py:109,143-148)
-  LV_TRY(ce_bwd(P->logits, V, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, st));
   const float* hd = dout.mode ? P->hdrop_d : P->h_d;
   {
-    Staged sdl = stage(P, Mat{P->logits, rd, V, V}, st, &status);
+    // tensor-core path: dlogits is produced directly as the split-bf16 operand (no fp32 round trip)
+    const bool tc_dl = P->use_tc && rd >= 32 && nh >= 16 && V >= 32;
+    Staged sdl;
+    if (tc_dl) {
+      sdl = stage_alloc(P, rd, V, &status);
+      LV_TRY(status);
+      LV_TRY(ce_bwd_split(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, const_cast<uint16_t*>(sdl.tc.hi),
+                          const_cast<uint16_t*>(sdl.tc.lo), sdl.tc.ld, st));
+    } else {
+      LV_TRY(ce_bwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, st));
+      sdl = stage(P, Mat{P->logits, rd, V, P->ldl}, st, &status);
+    }
     Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
     Staged sh = stage(P, Mat{hd, rd, nh, nh}, st, &status);
     LV_TRY(status);
     // dH_drop [rd, nh] = dlogits · W_pred
     LV_TRY(mm(P, sdl, false, swp, true, P->dh_d, nh, (int)rd, nh, V, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
     // dW_pred [V, nh] = dlogitsᵀ · H_drop
-    LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
+              P->dec_wgrad_passes, st));
   }
   P->arena_off = 0;  // dlogits staging no longer needed
 
@@ -521,13 +557,13 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     LV_TRY(status);
     // dW_ih[:, :ni] = dGᵀ · X   ;  dW_ih[:, ni:] = dzbᵀ · z
     LV_TRY(mm(P, sdg, true, sxd, true, gr->p[D_WIH], ni + nz, 4 * nh, ni, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
-              3, st));
+              P->dec_wgrad_passes, st));
     LV_TRY(gemm_f32(P->dzb, 1, 4 * nh, P->z, 1, nz, gr->p[D_WIH] + ni, ni + nz, 4 * nh, nz, Bd, 1.f, 0.f, nullptr,
                     nullptr, 0, st));
     // dW_hh = Σ_t dG_tᵀ h_{t-1}: rows t>=1 pair with h_d[t-1]; t=0 pairs with h0
     if (Td > 1)
       LV_TRY(mm(P, sub(sdg, Bd, rd - Bd, 0, 4 * nh), true, sub(shd, 0, rd - Bd, 0, nh), true, gr->p[D_WHH], nh,
-                4 * nh, nh, (int)(rd - Bd), 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+                4 * nh, nh, (int)(rd - Bd), 1.f, 0.f, nullptr, nullptr, 0, P->dec_wgrad_passes, st));
     LV_TRY(gemm_f32(P->dgates_d, 1, 4 * nh, P->h0, 1, nh, gr->p[D_WHH], nh, 4 * nh, nh, Bd, 1.f,
                     Td > 1 ? 1.f : 0.f, nullptr, nullptr, 0, st));
     // dX = dG · W_ih[:, :ni]  -> dense decoder embedding gradient (row V-1 = padding_idx, no grad)
@@ -559,7 +595,8 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   else
     LV_TRY(lstm_backward_steps(w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
                                P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, nh, false, st));
-  LV_TRY(col_sum(P->dgates_e, (int)re, 4 * nh, gr->p[E_BIH], gr->p[E_BHH], st));
+  LV_TRY(time_sum(P->dgates_e, Te, B, 4 * nh, P->dzb, st));   // Σ_t first (131 K threads), then Σ_b over B rows
+  LV_TRY(col_sum(P->dzb, B, 4 * nh, gr->p[E_BIH], gr->p[E_BHH], st));
   {
     Staged sdg = stage(P, Mat{P->dgates_e, re, 4 * nh, 4 * nh}, st, &status);
     Staged sxe = stage(P, Mat{P->xe, re, ni, ni}, st, &status);
@@ -614,7 +651,12 @@ int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, con
                                   nullptr, nullptr, nullptr, stream));
   LV_CUDA(cudaMemcpyAsync(out_scalars, P->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   LV_TRY(fill(P->dc0t, 1.f / (float)d.B, d.B, st));
-  LV_TRY(lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, stream));
+  // decoder WEIGHT gradients are never applied in this loop (text.py:387 steps the encoder only); they enter
+  // the update through the clip norm alone (text.py:385), for which one bf16 pass is ample (norm error ~1e-5)
+  P->dec_wgrad_passes = 1;
+  const int rb = lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, stream);
+  P->dec_wgrad_passes = 3;
+  LV_TRY(rb);
   // text.py:385 clip over all 13 grads; :387 encoder-only SGD step
   LV_TRY(clip_sgd_step(w->p, g.p, counts, LAGVAE_TEXT_NPARAM, 6, max_norm, lr, 0, out_scalars + 3,
                        P->clip_scratch, st));

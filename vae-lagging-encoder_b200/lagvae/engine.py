@@ -231,7 +231,7 @@ class TextEngine:
         G = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
         cnt = (C.c_int64 * n)(*[g.numel() for g in grads])
         norm = torch.empty(1, dtype=torch.float32, device=self.device)
-        scratch = torch.empty(4096, dtype=torch.uint8, device=self.device)
+        scratch = torch.empty(16384, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_clip_sgd_step(P, G, cnt, n, n_update, float(max_norm), float(lr),
                                                    1 if scale_all else 0, be.ptr(norm), be.ptr(scratch), _stream()),
