@@ -134,7 +134,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // the whole warp runs the (uniform) loop; one elected lane issues the copies
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (three ? 4u : 2u) * TILE_BYTES;
@@ -145,38 +146,41 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
           const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
-          ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
           const int k0 = kb * BK;
-          if (!A_MN) {
-            ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), k0, m0);
-            if (three) ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), k0, m0);
-          } else {  // stored [K, M]: two 64(M) x 64(K) boxes
-            ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), m0, k0);
-            ptx::tma_load_2d(sa_hi + TILE_BYTES / 2, &tm_a_hi, full_bar(stage), m0 + 64, k0);
-            if (three) {
-              ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), m0, k0);
-              ptx::tma_load_2d(sa_lo + TILE_BYTES / 2, &tm_a_lo, full_bar(stage), m0 + 64, k0);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
+            if (!A_MN) {
+              ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), k0, m0);
+              if (three) ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), k0, m0);
+            } else {  // stored [K, M]: two 64(M) x 64(K) boxes
+              ptx::tma_load_2d(sa_hi, &tm_a_hi, full_bar(stage), m0, k0);
+              ptx::tma_load_2d(sa_hi + TILE_BYTES / 2, &tm_a_hi, full_bar(stage), m0 + 64, k0);
+              if (three) {
+                ptx::tma_load_2d(sa_lo, &tm_a_lo, full_bar(stage), m0, k0);
+                ptx::tma_load_2d(sa_lo + TILE_BYTES / 2, &tm_a_lo, full_bar(stage), m0 + 64, k0);
+              }
+            }
+            if (!B_MN) {
+              ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), k0, n0);
+              if (three) ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), k0, n0);
+            } else {
+              ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), n0, k0);
+              ptx::tma_load_2d(sb_hi + TILE_BYTES / 2, &tm_b_hi, full_bar(stage), n0 + 64, k0);
+              if (three) {
+                ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), n0, k0);
+                ptx::tma_load_2d(sb_lo + TILE_BYTES / 2, &tm_b_lo, full_bar(stage), n0 + 64, k0);
+              }
             }
           }
-          if (!B_MN) {
-            ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), k0, n0);
-            if (three) ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), k0, n0);
-          } else {
-            ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), n0, k0);
-            ptx::tma_load_2d(sb_hi + TILE_BYTES / 2, &tm_b_hi, full_bar(stage), n0 + 64, k0);
-            if (three) {
-              ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), n0, k0);
-              ptx::tma_load_2d(sb_lo + TILE_BYTES / 2, &tm_b_lo, full_bar(stage), n0 + 64, k0);
-            }
-          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit
+    {
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the 128-B swizzle row.
       // MN-major: 64-element chunks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), +2048 B per UMMA_K.
@@ -195,26 +199,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           ptx::tc_fence_after();
           const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
           const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + k * A_KSTEP, A_LBO, A_SBO);
-            const uint64_t db_hi = ptx::make_smem_desc_sw128(sb_hi + k * B_KSTEP, B_LBO, B_SBO);
-            ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
-            if (three) {
-              const uint64_t da_lo = ptx::make_smem_desc_sw128(sa_lo + k * A_KSTEP, A_LBO, A_SBO);
-              const uint64_t db_lo = ptx::make_smem_desc_sw128(sb_lo + k * B_KSTEP, B_LBO, B_SBO);
-              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + k * A_KSTEP, A_LBO, A_SBO);
+              const uint64_t db_hi = ptx::make_smem_desc_sw128(sb_hi + k * B_KSTEP, B_LBO, B_SBO);
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+              if (three) {
+                const uint64_t da_lo = ptx::make_smem_desc_sw128(sa_lo + k * A_KSTEP, A_LBO, A_SBO);
+                const uint64_t db_lo = ptx::make_smem_desc_sw128(sb_lo + k * B_KSTEP, B_LBO, B_SBO);
+                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+              }
             }
+            ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+            if (kb == k_blks - 1) ptx::umma_commit(tfull_bar(acc));  // accumulator complete
           }
-          ptx::umma_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar(acc));  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue ================================
     // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose -> row-contiguous global stores:

@@ -129,6 +129,7 @@ __device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, 
 // ---- MMA issuer: one K sweep for m-tile mt ------------------------------------------------------
 constexpr int NACC = 4;  // independent TMEM accumulators per m-tile (one per K sub-step): no dependent-accumulate chain
 
+// called by the WHOLE MMA warp (uniform control flow); one elected lane issues the tensor-core work
 template <int NB>
 __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeState& ps, uint32_t d_tmem,
                                          uint32_t acc_bar) {
@@ -140,21 +141,24 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
     ptx::tc_fence_after();
     const uint32_t sa = sm.a_base + ps.stage * STAGE_BYTES;
     const uint32_t sw = sm.w_base + (uint32_t)(kb * 2) * WT;
+    if (ptx::elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-      const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + A_PART + k * 32, 16, 1024);
-      const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
-      const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
-      const uint32_t d = d_tmem + (uint32_t)(k * NB);
-      ptx::umma_f16(d, a_hi, b_hi, idesc, kb ? 1u : 0u);
-      ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
-      ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+        const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + A_PART + k * 32, 16, 1024);
+        const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
+        const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
+        const uint32_t d = d_tmem + (uint32_t)(k * NB);
+        ptx::umma_f16(d, a_hi, b_hi, idesc, kb ? 1u : 0u);
+        ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
+        ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+      }
+      ptx::umma_commit(sm.empty(ps.stage, a.NS));
+      if (kb == a.KB - 1) ptx::umma_commit(acc_bar);
     }
-    ptx::umma_commit(sm.empty(ps.stage, a.NS));
+    __syncwarp();
     if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
   }
-  ptx::umma_commit(acc_bar);
 }
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[8]) {
@@ -236,10 +240,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
     if (warp >= 5) {
       for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
-      if (lane == 0)
-        for (int mt = 0; mt < a.m_tiles; ++mt)
-          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32 * NACC), sm.acc(mt, a.NS));
-      __syncwarp();
+      for (int mt = 0; mt < a.m_tiles; ++mt)
+        mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32 * NACC), sm.acc(mt, a.NS));
     } else {
       float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
       for (int mt = 0; mt < a.m_tiles; ++mt) {
@@ -359,10 +361,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
       if (has_rec)
         for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
-      if (has_rec && lane == 0)
+      if (has_rec)
         for (int mt = 0; mt < a.m_tiles; ++mt)
           mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8 * NACC), sm.acc(mt, a.NS));
-      __syncwarp();
     } else {
       for (int mt = 0; mt < a.m_tiles; ++mt) {
         const int b = mt * 64 + warp * 16 + lane;

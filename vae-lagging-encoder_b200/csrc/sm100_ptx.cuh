@@ -13,6 +13,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// one elected lane of a fully converged warp (keeps the surrounding code warp-uniform, so descriptors and
+// addresses stay in uniform registers: no per-instruction R2UR round trips in the MMA / TMA issue loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(p));
+  return p != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
