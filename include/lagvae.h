@@ -186,6 +186,11 @@ int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, co
                          const lagvae_dropout* drop, float* dc, float* dh_rec, float* dgates, int want_init,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Profiling aid: when set (device uint64 buffer, >= 8*(Tn+1) words), CTA 0 of the persistent LSTM kernels records
+ * clock64() at 5 points of every time step ([step][8]: start, first operand stage landed, MMAs issued,
+ * accumulators complete, epilogue stores issued).  NULL disables (default). */
+void lagvae_debug_trace_buffer(void* dev_u64, size_t words);
+
 /* fp32 [rows, cols] (ld) -> bf16 hi/lo [rows, ld_out] (zero padded columns cols..ld_out). */
 int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, void* stream);

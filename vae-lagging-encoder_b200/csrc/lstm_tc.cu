@@ -26,13 +26,14 @@ namespace {
 
 constexpr int NTHREADS = 288;             // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
 constexpr int NPROD = 128;
-constexpr int A_PART = 64 * 128;          // 8 KiB: 64 rows x 128 B (64 bf16 of K)
-constexpr int STAGE_BYTES = 2 * A_PART;   // hi + lo
+constexpr int MAX_NS = 16;                // ring stages (barrier slots)
 constexpr int MAX_MT = 4;                 // m-tiles of 64 batch rows (Bd <= 256; 4 accumulator slots x 32 cols each)
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB
 
 struct RecArgs {
   int nh, Bd, Tn, KP, KB, NS, m_tiles;
+  int part_bytes;                // bytes of one operand part of a ring stage = rows_alloc x 128 (rows_alloc = Bd rounded to 8, <= 64)
+  unsigned long long* dbg;       // optional clock64 trace of CTA 0: [step][8]
   unsigned* bar;                 // grid barrier counter (host-zeroed)
   __nv_bfloat16* abuf;           // [2 slots][2 parts][Bd][KP] streamed operand (h or dG), bf16 hi/lo
   const float* w_hh;             // [4nh, nh]
@@ -58,15 +59,14 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// cooperative-groups style grid barrier on a monotonically increasing counter
+// grid barrier on a monotonically increasing counter: bar.sync orders the CTA's stores before thread 0's
+// release-add (cumulative), the acquire-poll orders them before every later load of the other CTAs
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     while (ld_acquire_u32(bar) < target) {
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -111,13 +111,13 @@ __device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, 
   const int64_t part_stride = (int64_t)a.Bd * a.KP;
   for (int kb = 0; kb < a.KB; ++kb) {
     ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
-    const uint32_t sbase = sm.a_base + ps.stage * STAGE_BYTES;
+    const uint32_t sbase = sm.a_base + ps.stage * 2 * a.part_bytes;
     for (int id = ptid; id < 2 * per_part; id += NPROD) {
       const int part = id >= per_part;
       const int rem = id - part * per_part;
       const int r = rem >> 3, c = rem & 7;
       const __nv_bfloat16* src = slot + part * part_stride + (int64_t)(mt * 64 + r) * a.KP + kb * 64 + c * 8;
-      ptx::cp_async_cg16(sbase + part * A_PART + sw128(r, c), src);
+      ptx::cp_async_cg16(sbase + part * a.part_bytes + sw128(r, c), src);
     }
     // asynchronous arrive: fires when this thread's copies above have landed (no blocking wait, so every
     // ring stage is in flight at once); the consumer issues the generic->async proxy fence after its wait
@@ -139,13 +139,13 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
     ptx::mbar_wait(sm.full(ps.stage), ps.phase);
     ptx::fence_proxy_async_smem();   // cp.async (generic proxy) writes -> visible to the UMMA (async proxy) reads
     ptx::tc_fence_after();
-    const uint32_t sa = sm.a_base + ps.stage * STAGE_BYTES;
+    const uint32_t sa = sm.a_base + ps.stage * 2 * a.part_bytes;
     const uint32_t sw = sm.w_base + (uint32_t)(kb * 2) * WT;
     if (ptx::elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-        const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + A_PART + k * 32, 16, 1024);
+        const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + a.part_bytes + k * 32, 16, 1024);
         const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
         const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
         const uint32_t d = d_tmem + (uint32_t)(k * NB);
@@ -171,9 +171,8 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst_hi, __nv_bfloat1
 
 __device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm, int tmem_cols, uint32_t* slot_ptr) {
   const int warp = threadIdx.x >> 5;
-  // zero the ring (rows beyond the batch must read as zero)
-  for (int i = threadIdx.x; i < a.NS * STAGE_BYTES / 16; i += NTHREADS)
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sm.a_base + i * 16), "r"(0u) : "memory");
+  // ring rows beyond the batch are never written: the UMMA reads 64 rows, but D row i depends on A row i only and
+  // rows >= Bd of D are never read back, so whatever aliases there (next part / next stage / W tiles) is harmless
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.NS; ++s) {
       ptx::mbar_init(sm.full(s), NPROD);
@@ -197,9 +196,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NB = 32, WT = NB * 128;
   Smem sm;
-  sm.w_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  sm.a_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
-  sm.bar_base = sm.a_base + (uint32_t)a.NS * STAGE_BYTES;
+  sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
+  sm.bar_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, u0 = blockIdx.x * 8;
@@ -234,14 +233,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
   grid_barrier(a.bar, (++epoch) * gridDim.x);
 
   PipeState ps{0, 0};
+  const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   for (int t = 0; t < a.Tn; ++t) {
+    if (trace && threadIdx.x == 0) a.dbg[t * 8 + 0] = clock64();                 // step start (barrier exit)
     const __nv_bfloat16* rd = a.abuf + (int64_t)((t + 1) & 1) * slot_elems;
     __nv_bfloat16* wr = a.abuf + (int64_t)(t & 1) * slot_elems;
     if (warp >= 5) {
       for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
+      if (trace && lane == 0) {   // first stage of this step landed?
+        ptx::mbar_wait(sm.full(ps.stage), ps.phase);
+        a.dbg[t * 8 + 1] = clock64();
+      }
       for (int mt = 0; mt < a.m_tiles; ++mt)
         mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32 * NACC), sm.acc(mt, a.NS));
+      if (trace && lane == 0) a.dbg[t * 8 + 2] = clock64();                      // all MMAs issued
     } else {
       float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
       for (int mt = 0; mt < a.m_tiles; ++mt) {
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
         }
         ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)(t & 1));
         ptx::tc_fence_after();
+        if (trace && threadIdx.x == 0 && mt == 0) a.dbg[t * 8 + 3] = clock64();  // accumulators complete
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = 0.f;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
         }
       }
       ptx::tc_fence_before();
+      if (trace && threadIdx.x == 0) a.dbg[t * 8 + 4] = clock64();               // epilogue stores issued
     }
     grid_barrier(a.bar, (++epoch) * gridDim.x);
     ptx::tc_fence_after();
@@ -323,9 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NB = 8, WT = NB * 128;
   Smem sm;
-  sm.w_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  sm.a_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
-  sm.bar_base = sm.a_base + (uint32_t)a.NS * STAGE_BYTES;
+  sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
+  sm.bar_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, Tn = a.Tn, u0 = blockIdx.x * 8;
@@ -352,7 +360,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
   unsigned epoch = 0;
   PipeState ps{0, 0};
   const int nsteps = Tn + (a.want_init ? 1 : 0);
+  const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   for (int s = 0; s < nsteps; ++s) {
+    if (trace && threadIdx.x == 0) a.dbg[s * 8 + 0] = clock64();
     const int t = Tn - 1 - s;            // t = -1 on the extra step that only produces d h_{-1}
     const bool has_rec = s > 0;
     const __nv_bfloat16* rd = a.abuf + (int64_t)((s + 1) & 1) * slot_elems;
@@ -361,9 +371,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
       if (has_rec)
         for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
-      if (has_rec)
+      if (has_rec) {
+        if (trace && lane == 0) {
+          ptx::mbar_wait(sm.full(ps.stage), ps.phase);
+          a.dbg[s * 8 + 1] = clock64();
+        }
         for (int mt = 0; mt < a.m_tiles; ++mt)
           mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8 * NACC), sm.acc(mt, a.NS));
+        if (trace && lane == 0) a.dbg[s * 8 + 2] = clock64();
+      }
     } else {
       for (int mt = 0; mt < a.m_tiles; ++mt) {
         const int b = mt * 64 + warp * 16 + lane;
@@ -396,6 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
         if (has_rec) {
           ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)((s - 1) & 1));
           ptx::tc_fence_after();
+          if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
 #pragma unroll
           for (int sl = 0; sl < NACC; ++sl) {
             uint32_t r[8];
@@ -440,6 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
         }
       }
       ptx::tc_fence_before();
+      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
     }
     grid_barrier(a.bar, (++epoch) * gridDim.x);
     ptx::tc_fence_after();
@@ -453,14 +471,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
 // host side
 // =================================================================================================
 struct LstmTcState {
-  int nh, G, KPf, KPb, NSf, NSb, max_bd;
-  size_t smem_f, smem_b;
+  int nh, G, KPf, KPb, max_bd;
+  int64_t wf, wb;  // resident weight bytes (forward / backward)
   __nv_bfloat16* abuf;
   unsigned* bar;
   bool configured;
 };
 
-static bool shape_supported(const lagvae_text_dims& d, int* nsf, int* nsb, size_t* smf, size_t* smb) {
+constexpr int64_t MISC_BYTES = 1024 /*align slack*/ + 8 * (2 * MAX_NS + MAX_MT + 1) + 64;
+
+static unsigned long long* g_dbg = nullptr;   // optional device trace buffer (lagvae_debug_trace_buffer)
+static size_t g_dbg_words = 0;
+void lstm_tc_set_debug(void* p, size_t words) {
+  g_dbg = (unsigned long long*)p;
+  g_dbg_words = words;
+}
+
+// ring geometry for a launch: stage = 2 parts (hi, lo) of rows_alloc x 128 B
+static bool ring_geometry(int64_t wbytes, int Bd, int KB, int* part_bytes, int* ns, size_t* smem) {
+  const int rows_alloc = Bd >= 64 ? 64 : (int)round_up(Bd, 8);
+  const int64_t stage = 2 * (int64_t)rows_alloc * 128;
+  int64_t n = (SMEM_LIMIT - wbytes - MISC_BYTES) / stage;
+  n = std::min<int64_t>(n, MAX_NS);
+  n = std::min<int64_t>(n, std::max(KB, 2));
+  if (n < 2) return false;
+  *part_bytes = rows_alloc * 128;
+  *ns = (int)n;
+  *smem = (size_t)(wbytes + n * stage + MISC_BYTES);
+  return true;
+}
+
+static bool shape_supported(const lagvae_text_dims& d) {
   const int nh = d.nh;
   if (nh % 8 != 0 || nh < 64) return false;
   int sms = 0, dev = 0;
@@ -470,15 +511,9 @@ static bool shape_supported(const lagvae_text_dims& d, int* nsf, int* nsb, size_
   if ((int64_t)d.B * d.ns > 64 * MAX_MT) return false;
   const int KPf = (int)round_up(nh, 64), KPb = (int)round_up(4 * nh, 64);
   const int64_t wf = (int64_t)(KPf / 64) * 2 * 32 * 128, wb = (int64_t)(KPb / 64) * 2 * 8 * 128;
-  const int64_t misc = 1024 + 8 * (2 * 8 + MAX_MT) + 64;
-  const int nf = (int)std::min<int64_t>(8, (SMEM_LIMIT - wf - misc) / STAGE_BYTES);
-  const int nb = (int)std::min<int64_t>(8, (SMEM_LIMIT - wb - misc) / STAGE_BYTES);
-  if (nf < 2 || nb < 2) return false;
-  *nsf = nf;
-  *nsb = nb;
-  *smf = (size_t)(wf + (int64_t)nf * STAGE_BYTES + misc);
-  *smb = (size_t)(wb + (int64_t)nb * STAGE_BYTES + misc);
-  return true;
+  int pb, ns;
+  size_t sm;
+  return ring_geometry(wf, 64, KPf / 64, &pb, &ns, &sm) && ring_geometry(wb, 64, KPb / 64, &pb, &ns, &sm);
 }
 
 size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc) {
@@ -490,9 +525,7 @@ size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc) {
 int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_bytes, LstmTcState** out) {
   *out = nullptr;
   if (!use_tc) return LAGVAE_OK;
-  int nsf = 0, nsb = 0;
-  size_t smf = 0, smb = 0;
-  if (!shape_supported(d, &nsf, &nsb, &smf, &smb)) return LAGVAE_OK;
+  if (!shape_supported(d)) return LAGVAE_OK;
   if (ws_bytes < lstm_tc_workspace_bytes(d, true)) {
     set_error("lstm_tc: workspace too small");
     return LAGVAE_E_WORKSPACE;
@@ -503,10 +536,8 @@ int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_b
   s->G = d.nh / 8;
   s->KPf = (int)round_up(d.nh, 64);
   s->KPb = (int)round_up(4 * d.nh, 64);
-  s->NSf = nsf;
-  s->NSb = nsb;
-  s->smem_f = smf;
-  s->smem_b = smb;
+  s->wf = (int64_t)(s->KPf / 64) * 2 * 32 * 128;
+  s->wb = (int64_t)(s->KPb / 64) * 2 * 8 * 128;
   s->max_bd = d.B * d.ns;
   s->bar = (unsigned*)ws;
   s->abuf = (__nv_bfloat16*)((char*)ws + 1024);
@@ -519,8 +550,8 @@ void lstm_tc_destroy(LstmTcState* s) { delete s; }
 
 static int configure(LstmTcState* s) {
   if (s->configured) return LAGVAE_OK;
-  LV_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_f));
-  LV_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_b));
+  LV_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  LV_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   s->configured = true;
   return LAGVAE_OK;
 }
@@ -531,15 +562,18 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_forward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
-  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPf; a.KB = s->KPf / 64; a.NS = s->NSf;
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPf; a.KB = s->KPf / 64;
   a.m_tiles = (int)cdiv(Bd, 64);
+  size_t smem = 0;
+  LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
+  a.dbg = (g_dbg && g_dbg_words >= (size_t)Tn * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
   a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   // the K padding columns of the streamed buffer must be zero
   if (s->KPf != s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPf * 2, st));
   void* args[] = {(void*)&a};
-  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, s->smem_f, st));
+  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
   return LAGVAE_OK;
 }
@@ -550,15 +584,18 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_backward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
-  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPb; a.KB = s->KPb / 64; a.NS = s->NSb;
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPb; a.KB = s->KPb / 64;
   a.m_tiles = (int)cdiv(Bd, 64);
+  size_t smem = 0;
+  LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
+  a.dbg = (g_dbg && g_dbg_words >= (size_t)(Tn + 1) * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
   a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;
   a.dh_rec_out = dh_rec; a.dgates = dgates; a.want_init = want_init ? 1 : 0;
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   if (s->KPb != 4 * s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPb * 2, st));
   void* args[] = {(void*)&a};
-  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, s->smem_b, st));
+  LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
   return LAGVAE_OK;
 }

@@ -724,6 +724,8 @@ int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, co
   return r;
 }
 
+void lagvae_debug_trace_buffer(void* dev_u64, size_t words) { lstm_tc_set_debug(dev_u64, words); }
+
 int lagvae_gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
                     float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, const float* bias_n,
                     const float* bias_rows, int bias_period, void* stream) {

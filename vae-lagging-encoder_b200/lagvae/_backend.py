@@ -60,6 +60,7 @@ PROTOTYPES = {
     "lagvae_lstm_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _sz, _vp]),
     "lagvae_lstm_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _vp, _i,
                                   _vp, _sz, _vp]),
+    "lagvae_debug_trace_buffer": (None, [_vp, _sz]),
     "lagvae_gemm_f32": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp]),
     "lagvae_gemm_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _f, _f,
                             _vp, _vp, _i, _vp, _vp]),
