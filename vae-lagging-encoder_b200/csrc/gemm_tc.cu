@@ -227,7 +227,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // every store instruction of a warp covers 4 rows x 128 B (vector path) or 1 row x 128 B (unaligned C).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     float* cst = (float*)(smem_raw + (bar_base + 256 - ptx::smem_u32(smem_raw))) + (warp - 2) * 32 * CSTRIDE;
-    const bool vec_ok = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((((uintptr_t)g.bias_n) & 15) == 0);
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((((uintptr_t)g.bias_n) & 15) == 0) &&
+                        (g.bias_rows == nullptr || (((g.N & 3) == 0) && ((((uintptr_t)g.bias_rows) & 15) == 0)));
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -261,10 +262,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
               const float* brow = g.bias_rows ? g.bias_rows + (int64_t)(row % g.bias_period) * g.N : nullptr;
               if (col + 3 < g.N) {
                 if (g.bias_n) { const float4 b = *(const float4*)(g.bias_n + col); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-                if (brow) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) vp[q] += brow[col + q];
-                }
+                if (brow) { const float4 b = *(const float4*)(brow + col); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
                 if (g.beta != 0.f) { const float4 o = *(const float4*)dst; v.x += g.beta * o.x; v.y += g.beta * o.y; v.z += g.beta * o.z; v.w += g.beta * o.w; }
                 *(float4*)dst = v;
               } else {

@@ -138,25 +138,42 @@ int gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t
 // ---------------------------------------------------------------------------------------------
 // fp32 -> bf16 hi/lo split (operand staging for gemm_tc)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 pack_bf16x4(const __nv_bfloat16 (&v)[4]) {
+  uint2 r;
+  r.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
+  r.y = (uint32_t)__bfloat16_as_ushort(v[2]) | ((uint32_t)__bfloat16_as_ushort(v[3]) << 16);
+  return r;
+}
+// 4 elements per thread: float4 load (when the source row is 16-B aligned), two 8-B stores
 __global__ void k_split_bf16(const float* __restrict__ src, int64_t ld, int rows, int cols,
                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                              int64_t ld_out) {
-  const int64_t n = (int64_t)rows * ld_out;
+  const int64_t q_per_row = ld_out >> 2;   // ld_out % 8 == 0
+  const int64_t n = (int64_t)rows * q_per_row;
+  const bool vec = ((ld & 3) == 0) && ((((uintptr_t)src) & 15) == 0);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / ld_out;
-    const int c = (int)(i - r * ld_out);
-    const float v = (c < cols) ? src[r * ld + c] : 0.f;
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    const int64_t r = i / q_per_row;
+    const int c = (int)(i - r * q_per_row) * 4;
+    float v[4];
+    if (vec && c + 3 < cols) {
+      const float4 x = *(const float4*)(src + r * ld + c);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c + j < cols) ? src[r * ld + c + j] : 0.f;
+    }
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    *(uint2*)(hi + r * ld_out + c) = pack_bf16x4(h);
+    *(uint2*)(lo + r * ld_out + c) = pack_bf16x4(l);
   }
 }
 int split_bf16_launch(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, cudaStream_t st) {
   if (rows <= 0) return LAGVAE_OK;
-  const int64_t n = (int64_t)rows * ld_out;
+  const int64_t n = (int64_t)rows * (ld_out / 4);
   const int blocks = (int)std::min<int64_t>(cdiv(n, 256), 148 * 16);
   k_split_bf16<<<blocks, 256, 0, st>>>(src, ld, rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
   LV_LAUNCH_CHECK();
@@ -448,9 +465,25 @@ k_ce_fwd(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __r
   const int bd = row % Bd, t = row / Bd;
   const float* l = logits + (int64_t)row * ld;
   float m = -INFINITY, s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float xv = l[v];
-    if (xv > m) { s = s * expf(m - xv) + 1.f; m = xv; } else { s += expf(xv - m); }
+  const bool vec = ((ld & 3) == 0) && ((((uintptr_t)logits) & 15) == 0);
+  if (vec) {   // float4 loads (rows are 16-B aligned), exponentials against the running max of the 4-group
+    const int V4 = V >> 2;
+    const float4* l4 = (const float4*)l;
+    for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+      const float4 x = l4[q];
+      const float gm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+      if (gm > m) { s *= expf(m - gm); m = gm; }
+      s += expf(x.x - m) + expf(x.y - m) + expf(x.z - m) + expf(x.w - m);
+    }
+    for (int v = (V4 << 2) + threadIdx.x; v < V; v += blockDim.x) {
+      const float xv = l[v];
+      if (xv > m) { s = s * expf(m - xv) + 1.f; m = xv; } else { s += expf(xv - m); }
+    }
+  } else {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float xv = l[v];
+      if (xv > m) { s = s * expf(m - xv) + 1.f; m = xv; } else { s += expf(xv - m); }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -511,17 +544,30 @@ k_ce_bwd_split(const float* __restrict__ logits, int64_t ld, int V, const int64_
   const float* l = logits + (int64_t)row * ld;
   __nv_bfloat16* h = hi + (int64_t)row * ld_out;
   __nv_bfloat16* w = lo + (int64_t)row * ld_out;
-  for (int v = threadIdx.x; v < (int)ld_out; v += blockDim.x) {
-    float d = 0.f;
-    if (v < V) {
-      float p = expf(l[v] - L);
-      if (v == tgt) p -= 1.f;
-      d = p * g;
+  const bool vec = ((ld & 3) == 0) && ((((uintptr_t)logits) & 15) == 0);
+  for (int q = threadIdx.x; q < (int)(ld_out >> 2); q += blockDim.x) {
+    const int v0 = q * 4;
+    float xv[4];
+    if (vec && v0 + 3 < V) {
+      const float4 x4 = *(const float4*)(l + v0);
+      xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = (v0 + j < V) ? l[v0 + j] : -INFINITY;
     }
-    __nv_bfloat16 a, c;
-    split_bf16(d, a, c);
-    h[v] = a;
-    w[v] = c;
+    __nv_bfloat16 a[4], c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = 0.f;
+      if (v0 + j < V) {
+        float p = expf(xv[j] - L);
+        if (v0 + j == tgt) p -= 1.f;
+        d = p * g;
+      }
+      split_bf16(d, a[j], c[j]);
+    }
+    *(uint2*)(h + v0) = pack_bf16x4(a);
+    *(uint2*)(w + v0) = pack_bf16x4(c);
   }
 }
 int ce_bwd_split(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd, int ns,

@@ -27,7 +27,7 @@ namespace {
 constexpr int NTHREADS = 288;             // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
 constexpr int NPROD = 128;
 constexpr int MAX_NS = 16;                // ring stages (barrier slots)
-constexpr int MAX_MT = 4;                 // m-tiles of 64 batch rows (Bd <= 256; 4 accumulator slots x 32 cols each)
+constexpr int MAX_MT = 4;                 // m-tiles of 64 batch rows (Bd <= 256; forward uses 128 TMEM columns per m-tile)
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB
 
 struct RecArgs {
@@ -127,31 +127,36 @@ __device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, 
 }
 
 // ---- MMA issuer: one K sweep for m-tile mt ------------------------------------------------------
-constexpr int NACC = 4;  // independent TMEM accumulators per m-tile (one per K sub-step): no dependent-accumulate chain
+// Weight tile of one k-block = [2*NB rows x 64 k]: rows [0,NB) = bf16 hi of the NB resident columns, rows
+// [NB,2NB) = their lo parts.  Per K sub-step TWO MMAs instead of three:
+//     D[:, 0:2NB] += A_hi · [W_hi ; W_lo]ᵀ      (N = 2NB: hi·hi and hi·lo in one instruction)
+//     D[:, 0:NB]  += A_lo · W_hiᵀ               (N = NB)
+// and the epilogue adds D[:, 0:NB] + D[:, NB:2NB].  (tcgen05.mma with M=64 costs ~55 cycles whatever N <= 64
+// is — measured with the clock64 trace — so the instruction count is what matters.)
+constexpr int NACC = 2;  // accumulator slots per m-tile (alternating K sub-steps)
 
 // called by the WHOLE MMA warp (uniform control flow); one elected lane issues the tensor-core work
 template <int NB>
 __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeState& ps, uint32_t d_tmem,
                                          uint32_t acc_bar) {
-  constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(64, NB, 0, 0);
-  constexpr int WT = NB * 128;  // bytes of one weight tile (NB rows x 128 B)
+  constexpr uint32_t idesc_all = ptx::make_idesc_bf16_f32(64, 2 * NB, 0, 0);
+  constexpr uint32_t idesc_hi = ptx::make_idesc_bf16_f32(64, NB, 0, 0);
+  constexpr int WT2 = 2 * NB * 128;  // bytes of one merged weight tile
   for (int kb = 0; kb < a.KB; ++kb) {
     ptx::mbar_wait(sm.full(ps.stage), ps.phase);
     ptx::fence_proxy_async_smem();   // cp.async (generic proxy) writes -> visible to the UMMA (async proxy) reads
     ptx::tc_fence_after();
     const uint32_t sa = sm.a_base + ps.stage * 2 * a.part_bytes;
-    const uint32_t sw = sm.w_base + (uint32_t)(kb * 2) * WT;
+    const uint32_t sw = sm.w_base + (uint32_t)kb * WT2;
     if (ptx::elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
         const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + a.part_bytes + k * 32, 16, 1024);
-        const uint64_t b_hi = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
-        const uint64_t b_lo = ptx::make_smem_desc_sw128(sw + WT + k * 32, 16, 1024);
-        const uint32_t d = d_tmem + (uint32_t)(k * NB);
-        ptx::umma_f16(d, a_hi, b_hi, idesc, kb ? 1u : 0u);
-        ptx::umma_f16(d, a_hi, b_lo, idesc, 1u);
-        ptx::umma_f16(d, a_lo, b_hi, idesc, 1u);
+        const uint64_t b = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
+        const uint32_t d = d_tmem + (uint32_t)((k & (NACC - 1)) * 2 * NB);
+        ptx::umma_f16(d, a_hi, b, idesc_all, (kb > 0 || k >= NACC) ? 1u : 0u);
+        ptx::umma_f16(d, a_lo, b, idesc_hi, 1u);
       }
       ptx::umma_commit(sm.empty(ps.stage, a.NS));
       if (kb == a.KB - 1) ptx::umma_commit(acc_bar);
@@ -159,6 +164,26 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
     __syncwarp();
     if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
   }
+}
+
+// fast, accurate-to-~3e-7 gate non-linearities (ex2.approx based; the precise tanhf/expf paths cost ~4x more
+// instructions and the cell epilogue is on the per-time-step critical path)
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) {
+  const float t = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - t, 1.f + t), x);
+}
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[4]) {
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+  uint2 h, l;
+  h.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+  h.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+  l.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+  l.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+  *(uint2*)dst_hi = h;
+  *(uint2*)dst_lo = l;
 }
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[8]) {
@@ -194,18 +219,18 @@ __device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm
 // =================================================================================================
 __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NB = 32, WT = NB * 128;
+  constexpr int NB = 32, WT2 = 2 * NB * 128, TCOLS = NACC * 2 * NB;  // 128 TMEM columns per m-tile
   Smem sm;
   sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
-  sm.bar_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
+  sm.bar_base = sm.w_base + (uint32_t)a.KB * WT2;
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, u0 = blockIdx.x * 8;
-  const int need_cols = a.m_tiles * 32 * NACC;
+  const int need_cols = a.m_tiles * TCOLS;
   const int tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
 
-  // resident W_hh slice: tile (kb, part) = [32 rows x 64 k] bf16, rows n = gate*8 + uu
+  // resident W_hh slice: merged tile (kb) = [64 rows x 64 k] bf16: row n = gate*8 + uu (hi), row 32 + n (lo)
   for (int id = threadIdx.x; id < 32 * (a.KP / 8); id += NTHREADS) {
     const int n = id / (a.KP / 8), ck = id % (a.KP / 8);
     const int k0 = ck * 8;
@@ -214,8 +239,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (k0 + j < nh) ? src[j] : 0.f;
     const int kb = k0 >> 6, c = (k0 & 63) >> 3;
-    uint8_t* t_hi = gen_base + (size_t)(kb * 2) * WT + sw128(n, c);
-    store_bf16x8((__nv_bfloat16*)t_hi, (__nv_bfloat16*)(t_hi + WT), v);
+    uint8_t* tile = gen_base + (size_t)kb * WT2;
+    store_bf16x8((__nv_bfloat16*)(tile + sw128(n, c)), (__nv_bfloat16*)(tile + sw128(NB + n, c)), v);
   }
   common_prologue(a, sm, tmem_cols, nullptr);
   const uint32_t tmem_base = *(uint32_t*)(gen_base + (sm.tmem_slot(a.NS) - sm.w_base));
@@ -239,32 +264,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
     const __nv_bfloat16* rd = a.abuf + (int64_t)((t + 1) & 1) * slot_elems;
     __nv_bfloat16* wr = a.abuf + (int64_t)(t & 1) * slot_elems;
     if (warp >= 5) {
-      for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
+      for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT2>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
       if (trace && lane == 0) {   // first stage of this step landed?
         ptx::mbar_wait(sm.full(ps.stage), ps.phase);
         a.dbg[t * 8 + 1] = clock64();
       }
       for (int mt = 0; mt < a.m_tiles; ++mt)
-        mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 32 * NACC), sm.acc(mt, a.NS));
+        mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * TCOLS), sm.acc(mt, a.NS));
       if (trace && lane == 0) a.dbg[t * 8 + 2] = clock64();                      // all MMAs issued
     } else {
+      // epilogue: TMEM lane l (< 16) of warp w holds batch row 16w + l.  Lane l handles units 0-3 of that row,
+      // lane l + 16 handles units 4-7 (values handed over by shuffle): all 32 lanes of the warp do cell maths.
       float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
+      const int half = lane >> 4, ub = u0 + half * 4;
       for (int mt = 0; mt < a.m_tiles; ++mt) {
-        const int b = mt * 64 + warp * 16 + lane;
-        const bool valid = lane < 16 && b < Bd;
-        float pre[32], cp[8];
+        const int b = mt * 64 + warp * 16 + (lane & 15);
+        const bool valid = b < Bd;
+        float pre[16], cp[4];
         if (valid) {  // prefetch the input projection and c_{t-1} while the MMAs run
-          const float* g = gates_t + (int64_t)b * 4 * nh + u0;
+          const float* g = gates_t + (int64_t)b * 4 * nh + ub;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 x0 = *(const float4*)(g + q * nh), x1 = *(const float4*)(g + q * nh + 4);
-            pre[q * 8 + 0] = x0.x; pre[q * 8 + 1] = x0.y; pre[q * 8 + 2] = x0.z; pre[q * 8 + 3] = x0.w;
-            pre[q * 8 + 4] = x1.x; pre[q * 8 + 5] = x1.y; pre[q * 8 + 6] = x1.z; pre[q * 8 + 7] = x1.w;
+            const float4 x0 = *(const float4*)(g + q * nh);
+            pre[q * 4 + 0] = x0.x; pre[q * 4 + 1] = x0.y; pre[q * 4 + 2] = x0.z; pre[q * 4 + 3] = x0.w;
           }
-          const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + u0 : (a.c0 ? a.c0 + (int64_t)b * nh + u0 : nullptr);
+          const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + ub : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp[j] = cpp ? cpp[j] : 0.f;
+          for (int j = 0; j < 4; ++j) cp[j] = cpp ? cpp[j] : 0.f;
         }
         ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)(t & 1));
         ptx::tc_fence_after();
@@ -273,46 +300,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int sl = 0; sl < NACC; ++sl) {   // sum the independent accumulator slots
+        for (int sl = 0; sl < NACC * 2; ++sl) {   // NACC slots x {A·W_hi (+A_lo·W_hi), A_hi·W_lo}
           uint32_t r[32];
-          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 32 * NACC + sl * 32), r);
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * TCOLS + sl * 32), r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
         }
-        if (valid) {
-          float hv[8], cv[8], act[32];
+        // hand units 4-7 to the upper half-warp
+        float my[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float ig = sigmoidf_(pre[j] + acc[j]);
-            const float fg = sigmoidf_(pre[8 + j] + acc[8 + j]);
-            const float gg = tanhf(pre[16 + j] + acc[16 + j]);
-            const float og = sigmoidf_(pre[24 + j] + acc[24 + j]);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float up = __shfl_sync(0xffffffffu, acc[q * 8 + 4 + j], lane & 15);
+            my[q * 4 + j] = half ? up : acc[q * 8 + j];
+          }
+        if (valid) {
+          float hv[4], cv[4], act[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ig = fsigmoid(pre[j] + my[j]);
+            const float fg = fsigmoid(pre[4 + j] + my[4 + j]);
+            const float gg = ftanh(pre[8 + j] + my[8 + j]);
+            const float og = fsigmoid(pre[12 + j] + my[12 + j]);
             const float c = fg * cp[j] + ig * gg;
             cv[j] = c;
-            hv[j] = og * tanhf(c);
-            act[j] = ig; act[8 + j] = fg; act[16 + j] = gg; act[24 + j] = og;
+            hv[j] = og * ftanh(c);
+            act[j] = ig; act[4 + j] = fg; act[8 + j] = gg; act[12 + j] = og;
           }
-          float* g = gates_t + (int64_t)b * 4 * nh + u0;
+          __nv_bfloat16* d = wr + (int64_t)b * a.KP + ub;
+          store_bf16x4(d, d + (int64_t)Bd * a.KP, hv);          // next step's operand first
+          float* g = gates_t + (int64_t)b * 4 * nh + ub;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            *(float4*)(g + q * nh) = make_float4(act[q * 8], act[q * 8 + 1], act[q * 8 + 2], act[q * 8 + 3]);
-            *(float4*)(g + q * nh + 4) = make_float4(act[q * 8 + 4], act[q * 8 + 5], act[q * 8 + 6], act[q * 8 + 7]);
-          }
-          const int64_t o = ((int64_t)t * Bd + b) * nh + u0;
+          for (int q = 0; q < 4; ++q)
+            *(float4*)(g + q * nh) = make_float4(act[q * 4], act[q * 4 + 1], act[q * 4 + 2], act[q * 4 + 3]);
+          const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
           *(float4*)(a.c_all + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-          *(float4*)(a.c_all + o + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
           *(float4*)(a.h_all + o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *(float4*)(a.h_all + o + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
           if (a.hdrop_all) {
-            float hd[8];
+            float hd[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hd[j] = hv[j] * drop_factor(a.drop, ((uint64_t)b * a.Tn + t) * nh + u0 + j);
+            for (int j = 0; j < 4; ++j) hd[j] = hv[j] * drop_factor(a.drop, ((uint64_t)b * a.Tn + t) * nh + ub + j);
             *(float4*)(a.hdrop_all + o) = make_float4(hd[0], hd[1], hd[2], hd[3]);
-            *(float4*)(a.hdrop_all + o + 4) = make_float4(hd[4], hd[5], hd[6], hd[7]);
           }
-          __nv_bfloat16* d = wr + (int64_t)b * a.KP + u0;
-          store_bf16x8(d, d + (int64_t)Bd * a.KP, hv);
         }
       }
       ptx::tc_fence_before();
@@ -329,15 +360,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
 // =================================================================================================
 __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NB = 8, WT = NB * 128;
+  constexpr int NB = 8, WT2 = 2 * NB * 128, TCOLS = NACC * 2 * NB;   // 32 TMEM columns per m-tile
   Smem sm;
   sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
-  sm.bar_base = sm.w_base + (uint32_t)a.KB * 2 * WT;
+  sm.bar_base = sm.w_base + (uint32_t)a.KB * WT2;
   uint8_t* gen_base = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, Tn = a.Tn, u0 = blockIdx.x * 8;
-  const int need_cols = a.m_tiles * 8 * NACC;
+  const int need_cols = a.m_tiles * TCOLS;
   const int tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : 256));
 
   // resident W_hhᵀ slice: rows n = unit uu, K index = gate column k in [0, 4nh): W_hh[k, u0+uu]
@@ -348,8 +379,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (k0 + j < 4 * nh) ? a.w_hh[(int64_t)(k0 + j) * nh + u0 + n] : 0.f;
     const int kb = k0 >> 6, c = (k0 & 63) >> 3;
-    uint8_t* t_hi = gen_base + (size_t)(kb * 2) * WT + sw128(n, c);
-    store_bf16x8((__nv_bfloat16*)t_hi, (__nv_bfloat16*)(t_hi + WT), v);
+    uint8_t* tile = gen_base + (size_t)kb * WT2;   // merged tile: rows [0,8) hi, rows [8,16) lo
+    store_bf16x8((__nv_bfloat16*)(tile + sw128(n, c)), (__nv_bfloat16*)(tile + sw128(NB + n, c)), v);
   }
   common_prologue(a, sm, tmem_cols, nullptr);
   const uint32_t tmem_base = *(uint32_t*)(gen_base + (sm.tmem_slot(a.NS) - sm.w_base));
@@ -369,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
     __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
     if (warp >= 5) {
       if (has_rec)
-        for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT>(a, sm, ps, rd, mt, threadIdx.x - 160);
+        for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT2>(a, sm, ps, rd, mt, threadIdx.x - 160);
     } else if (warp == 4) {
       if (has_rec) {
         if (trace && lane == 0) {
@@ -377,7 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
           a.dbg[s * 8 + 1] = clock64();
         }
         for (int mt = 0; mt < a.m_tiles; ++mt)
-          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * 8 * NACC), sm.acc(mt, a.NS));
+          mma_pass<NB>(a, sm, ps, tmem_base + (uint32_t)(mt * TCOLS), sm.acc(mt, a.NS));
         if (trace && lane == 0) a.dbg[s * 8 + 2] = clock64();
       }
     } else {
@@ -414,9 +445,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
           ptx::tc_fence_after();
           if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
 #pragma unroll
-          for (int sl = 0; sl < NACC; ++sl) {
+          for (int sl = 0; sl < NACC * 2; ++sl) {   // NACC slots x {cols 0-7, cols 8-15}
             uint32_t r[8];
-            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 8 * NACC + sl * 8), r);
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * TCOLS + sl * 8), r);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) rec[j] += __uint_as_float(r[j]);
@@ -432,7 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
             for (int j = 0; j < 8; ++j) {
               const float ig = gt[j], fg = gt[8 + j], gg = gt[16 + j], og = gt[24 + j];
               const float dh = rec[j] + dhx[j];
-              const float tc = tanhf(cc[j]);
+              const float tc = ftanh(cc[j]);
               const float dct = dcv[j] + dh * og * (1.f - tc * tc);
               dg[j] = dct * gg * ig * (1.f - ig);
               dg[8 + j] = dct * cp[j] * fg * (1.f - fg);
