@@ -24,11 +24,14 @@ namespace lagvae {
 
 namespace {
 
-constexpr int NTHREADS = 288;             // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
-constexpr int NPROD = 128;
+constexpr int NTHREADS = 192;             // warps 0-3 epilogue, warp 4 MMA issuer, warp 5 TMA producer
 constexpr int MAX_NS = 16;                // ring stages (barrier slots)
 constexpr int MAX_MT = 4;                 // m-tiles of 64 batch rows (Bd <= 256; forward uses 128 TMEM columns per m-tile)
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB
+
+struct TMaps {
+  CUtensorMap m[4];   // [slot][part] views of the streamed operand: [Bd rows, KP cols] bf16, box 64 x rows_alloc, SWIZZLE_128B
+};
 
 struct RecArgs {
   int nh, Bd, Tn, KP, KB, NS, m_tiles;
@@ -103,25 +106,20 @@ struct PipeState {
   uint32_t phase;
 };
 
-template <int WTILE_BYTES>
-__device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, PipeState& ps,
-                                              const __nv_bfloat16* slot, int mt, int ptid) {
-  const int rows = min(64, a.Bd - mt * 64);
-  const int per_part = rows * 8;
-  const int64_t part_stride = (int64_t)a.Bd * a.KP;
+// whole producer warp (uniform); one elected lane issues two TMA loads (hi, lo part) per k-block.  TMA writes shared
+// memory through the async proxy, so the UMMA consumer needs no generic->async proxy fence per stage (that fence
+// waited for every in-flight copy and serialised the ring at one L2 round trip per k-block: profiles/README.md).
+__device__ __forceinline__ void producer_pass(const RecArgs& a, const Smem& sm, PipeState& ps, const TMaps& tm,
+                                              int slot, int mt) {
   for (int kb = 0; kb < a.KB; ++kb) {
     ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
     const uint32_t sbase = sm.a_base + ps.stage * 2 * a.part_bytes;
-    for (int id = ptid; id < 2 * per_part; id += NPROD) {
-      const int part = id >= per_part;
-      const int rem = id - part * per_part;
-      const int r = rem >> 3, c = rem & 7;
-      const __nv_bfloat16* src = slot + part * part_stride + (int64_t)(mt * 64 + r) * a.KP + kb * 64 + c * 8;
-      ptx::cp_async_cg16(sbase + part * a.part_bytes + sw128(r, c), src);
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(sm.full(ps.stage), 2u * (uint32_t)a.part_bytes);
+      ptx::tma_load_2d(sbase, &tm.m[slot * 2 + 0], sm.full(ps.stage), kb * 64, mt * 64);
+      ptx::tma_load_2d(sbase + a.part_bytes, &tm.m[slot * 2 + 1], sm.full(ps.stage), kb * 64, mt * 64);
     }
-    // asynchronous arrive: fires when this thread's copies above have landed (no blocking wait, so every
-    // ring stage is in flight at once); the consumer issues the generic->async proxy fence after its wait
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sm.full(ps.stage)) : "memory");
+    __syncwarp();
     if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
   }
 }
@@ -144,7 +142,6 @@ __device__ __forceinline__ void mma_pass(const RecArgs& a, const Smem& sm, PipeS
   constexpr int WT2 = 2 * NB * 128;  // bytes of one merged weight tile
   for (int kb = 0; kb < a.KB; ++kb) {
     ptx::mbar_wait(sm.full(ps.stage), ps.phase);
-    ptx::fence_proxy_async_smem();   // cp.async (generic proxy) writes -> visible to the UMMA (async proxy) reads
     ptx::tc_fence_after();
     const uint32_t sa = sm.a_base + ps.stage * 2 * a.part_bytes;
     const uint32_t sw = sm.w_base + (uint32_t)kb * WT2;
@@ -200,7 +197,7 @@ __device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm
   // rows >= Bd of D are never read back, so whatever aliases there (next part / next stage / W tiles) is harmless
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.NS; ++s) {
-      ptx::mbar_init(sm.full(s), NPROD);
+      ptx::mbar_init(sm.full(s), 1);
       ptx::mbar_init(sm.empty(s, a.NS), 1);
     }
     for (int m = 0; m < MAX_MT; ++m) ptx::mbar_init(sm.acc(m, a.NS), 1);
@@ -217,7 +214,7 @@ __device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm
 // =================================================================================================
 // forward
 // =================================================================================================
-__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a, const __grid_constant__ TMaps tm) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NB = 32, WT2 = 2 * NB * 128, TCOLS = NACC * 2 * NB;  // 128 TMEM columns per m-tile
   Smem sm;
@@ -254,6 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
     __nv_bfloat16* d = a.abuf + slot_elems + (int64_t)b * a.KP + u0;
     store_bf16x8(d, d + (int64_t)Bd * a.KP, v);
   }
+  ptx::fence_proxy_async_all();   // generic stores above are read by other CTAs' TMA (async proxy) after the barrier
   unsigned epoch = 0;
   grid_barrier(a.bar, (++epoch) * gridDim.x);
 
@@ -261,10 +259,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
   const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   for (int t = 0; t < a.Tn; ++t) {
     if (trace && threadIdx.x == 0) a.dbg[t * 8 + 0] = clock64();                 // step start (barrier exit)
-    const __nv_bfloat16* rd = a.abuf + (int64_t)((t + 1) & 1) * slot_elems;
     __nv_bfloat16* wr = a.abuf + (int64_t)(t & 1) * slot_elems;
-    if (warp >= 5) {
-      for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT2>(a, sm, ps, rd, mt, threadIdx.x - 160);
+    if (warp == 5) {
+      ptx::fence_proxy_async_all();   // h_{t-1} was written with generic stores by other SMs (acquired at the barrier)
+      for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass(a, sm, ps, tm, (t + 1) & 1, mt);
     } else if (warp == 4) {
       if (trace && lane == 0) {   // first stage of this step landed?
         ptx::mbar_wait(sm.full(ps.stage), ps.phase);
@@ -346,6 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
           }
         }
       }
+      ptx::fence_proxy_async_all();   // this thread's h_t stores -> visible to the async proxy (next step's TMA)
       ptx::tc_fence_before();
       if (trace && threadIdx.x == 0) a.dbg[t * 8 + 4] = clock64();               // epilogue stores issued
     }
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_fwd_tc(const RecArgs a) {
 // =================================================================================================
 // backward
 // =================================================================================================
-__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a, const __grid_constant__ TMaps tm) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NB = 8, WT2 = 2 * NB * 128, TCOLS = NACC * 2 * NB;   // 32 TMEM columns per m-tile
   Smem sm;
@@ -396,11 +395,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
     if (trace && threadIdx.x == 0) a.dbg[s * 8 + 0] = clock64();
     const int t = Tn - 1 - s;            // t = -1 on the extra step that only produces d h_{-1}
     const bool has_rec = s > 0;
-    const __nv_bfloat16* rd = a.abuf + (int64_t)((s + 1) & 1) * slot_elems;
     __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
-    if (warp >= 5) {
-      if (has_rec)
-        for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass<WT2>(a, sm, ps, rd, mt, threadIdx.x - 160);
+    if (warp == 5) {
+      if (has_rec) {
+        ptx::fence_proxy_async_all();
+        for (int mt = 0; mt < a.m_tiles; ++mt) producer_pass(a, sm, ps, tm, (s + 1) & 1, mt);
+      }
     } else if (warp == 4) {
       if (has_rec) {
         if (trace && lane == 0) {
@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a) {
           }
         }
       }
+      ptx::fence_proxy_async_all();   // dG_t stores -> async proxy (next step's TMA)
       ptx::tc_fence_before();
       if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
     }
@@ -587,6 +588,16 @@ static int configure(LstmTcState* s) {
   return LAGVAE_OK;
 }
 
+static int make_maps(const LstmTcState* s, int Bd, int KP, int part_bytes, TMaps* tm) {
+  for (int slot = 0; slot < 2; ++slot)
+    for (int part = 0; part < 2; ++part) {
+      const __nv_bfloat16* base = s->abuf + ((int64_t)slot * 2 + part) * Bd * KP;
+      LV_TRY(make_tmap_bf16_2d(&tm->m[slot * 2 + part], base, (uint64_t)Bd, (uint64_t)KP, (uint64_t)KP, 64,
+                               (uint32_t)(part_bytes / 128)));
+    }
+  return LAGVAE_OK;
+}
+
 int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,
                     float* c_all, float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd,
                     cudaStream_t st) {
@@ -603,7 +614,9 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   // the K padding columns of the streamed buffer must be zero
   if (s->KPf != s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPf * 2, st));
-  void* args[] = {(void*)&a};
+  TMaps tm;
+  LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
   return LAGVAE_OK;
@@ -625,7 +638,9 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   a.dh_rec_out = dh_rec; a.dgates = dgates; a.want_init = want_init ? 1 : 0;
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   if (s->KPb != 4 * s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPb * 2, st));
-  void* args[] = {(void*)&a};
+  TMaps tm;
+  LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
   return LAGVAE_OK;
