@@ -171,7 +171,9 @@ def test_clip_sgd_matches_torch():
 
 @pytest.mark.parametrize("nh,Bd,Tn,init,dropout", [(128, 16, 5, True, True), (1024, 32, 6, False, False),
                                                     (1024, 32, 4, True, True), (192, 70, 4, True, False),
-                                                    (64, 5, 3, False, True), (512, 130, 3, True, True)])
+                                                    (64, 5, 3, False, True), (512, 130, 3, True, True),
+                                                    (1024, 64, 3, True, True), (1024, 100, 3, True, False),
+                                                    (256, 8, 4, False, True), (512, 32, 5, True, True)])
 def test_lstm_persistent_tcgen05_matches_step_tier(nh, Bd, Tn, init, dropout):
     """Persistent tcgen05 recurrence (one cooperative launch) vs the launch-per-step fp32 tier."""
     be = _be()

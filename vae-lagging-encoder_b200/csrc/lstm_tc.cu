@@ -18,6 +18,7 @@
 #include "lstm_tc.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
 #include <new>
 
 namespace lagvae {
@@ -497,6 +498,316 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_bwd_tc(const RecArgs a, co
   if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
 }
 
+
+// =================================================================================================
+// v2: cluster K-split recurrence.  tcgen05.mma with M=64 costs ~58 cycles for any N <= 64 and N/2 cycles above
+// (scripts/microbench/mma_cost.cu), so the per-step MMA time is (#instructions) x 58: the v1 kernels (N = 32 / 8,
+// full K per CTA: 128-192 / 512-768 MMAs per step) are instruction-count bound.  v2 keeps the SAME unit ownership
+// and global data layout but lets a thread-block CLUSTER split K:
+//   forward : cluster of 4 CTAs = 32 units (128 gate columns).  CTA rank r holds W_hh[128 cols, K-slice r] (hi+lo
+//             merged: N = 256) and multiplies its quarter of h_{t-1}: 16 K sub-steps x 2 MMAs per time step.
+//   backward: cluster of 8 CTAs = 64 units.  CTA rank r holds W_hhᵀ[64 units, K-slice r of the 4nh gate columns]
+//             (N = 128) and multiplies its eighth of dG_{t+1}: 32 K sub-steps x 2 MMAs per time step (v1: 512).
+//   The partial products [Bd x NC] go TMEM -> shared memory; after a cluster barrier every CTA sums the NC/CS
+//   columns it owns over the CS peers through distributed shared memory (ld.shared::cluster) and runs the cell.
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
+template <bool FWD>
+struct V2Cfg {
+  static constexpr int CS = FWD ? 4 : 8;          // cluster size = K split
+  static constexpr int NOWN = FWD ? 32 : 8;       // result columns owned per CTA (8 units x 4 gates | 8 units)
+  static constexpr int NC = CS * NOWN;            // columns of the cluster (128 | 64)
+  static constexpr int NALL = 2 * NC;             // merged hi+lo weight rows = MMA N (256 | 128)
+  static constexpr int WT = NALL * 128;           // bytes of one weight tile (one 64-wide k-block)
+  static constexpr int PSTRIDE = NC + 4;          // floats per row of the partial buffer
+};
+
+template <bool FWD>
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const __grid_constant__ TMaps tm) {
+  using C = V2Cfg<FWD>;
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = a.nh, Bd = a.Bd, Tn = a.Tn;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = blockIdx.x / C::CS;                 // cluster index
+  const int u0 = blockIdx.x * 8;                     // owned units (same ownership as v1)
+  const int KBS = a.KB / C::CS;                      // k-blocks of this CTA's K slice
+  const int rows_alloc = a.part_bytes / 128;
+  Smem sm;
+  sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
+  const uint32_t p_base = sm.w_base + (uint32_t)KBS * C::WT;                       // partial buffer [m_tiles*rows][PSTRIDE] fp32
+  sm.bar_base = p_base + (uint32_t)(a.m_tiles * rows_alloc * C::PSTRIDE * 4);
+  uint8_t* gen_w = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
+  float* P = (float*)(smem_raw + (p_base - ptx::smem_u32(smem_raw)));
+  const int tmem_need = a.m_tiles * C::NALL;
+  const int tmem_cols = tmem_need <= 128 ? 128 : (tmem_need <= 256 ? 256 : 512);
+
+  // ---- resident weight slice -> merged [hi rows ; lo rows] UMMA B tiles -------------------------------------
+  {
+    const int kslice0 = (int)rank * KBS * 64;
+    const int nchunk = KBS * 8;                                // 16-B chunks (8 k) per row
+    for (int id = threadIdx.x; id < C::NC * nchunk; id += NTHREADS) {
+      int j, ck;
+      if (FWD) { j = id / nchunk; ck = id % nchunk; } else { j = id % C::NC; ck = id / C::NC; }
+      const int k0 = kslice0 + ck * 8;
+      float v[8];
+      if (FWD) {   // column j = q*32 + gate*8 + uu  <->  W_hh row gate*nh + 32*cl + 8q + uu ; K index = hidden unit
+        const int q = j >> 5, gate = (j >> 3) & 3, uu = j & 7;
+        const float* src = a.w_hh + (int64_t)(gate * nh + 32 * cl + 8 * q + uu) * nh + k0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (k0 + e < nh) ? src[e] : 0.f;
+      } else {     // row j = unit 64*cl + j ; K index = gate column k: W_hh[k, unit]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (k0 + e < 4 * nh) ? a.w_hh[(int64_t)(k0 + e) * nh + 64 * cl + j] : 0.f;
+      }
+      uint8_t* tile = gen_w + (size_t)(ck >> 3) * C::WT;
+      const int c = ck & 7;
+      store_bf16x8((__nv_bfloat16*)(tile + sw128(j, c)), (__nv_bfloat16*)(tile + sw128(C::NC + j, c)), v);
+    }
+  }
+  common_prologue(a, sm, tmem_cols, nullptr);
+  const uint32_t tmem_base = *(uint32_t*)(gen_w + (sm.tmem_slot(a.NS) - sm.w_base));
+  const int64_t slot_elems = (int64_t)2 * Bd * a.KP;
+  if (FWD) {   // publish h_{-1} (own 8 units, all rows) into slot 1
+    for (int b = threadIdx.x; b < Bd; b += NTHREADS) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = a.h0 ? a.h0[(int64_t)b * nh + u0 + j] : 0.f;
+      __nv_bfloat16* d = a.abuf + slot_elems + (int64_t)b * a.KP + u0;
+      store_bf16x8(d, d + (int64_t)Bd * a.KP, v);
+    }
+  } else {
+    for (int i = threadIdx.x; i < Bd * 8; i += NTHREADS) a.dc[(int64_t)(i >> 3) * nh + u0 + (i & 7)] = 0.f;
+  }
+  ptx::fence_proxy_async_all();
+  unsigned epoch = 0;
+  cluster_sync_all();                                // peers' smem (partial buffers, barriers) exist before any DSMEM access
+  grid_barrier(a.bar, (++epoch) * gridDim.x);
+
+  PipeState ps{0, 0};
+  const bool trace = a.dbg != nullptr && blockIdx.x == 0;
+  const int nsteps = FWD ? Tn : Tn + (a.want_init ? 1 : 0);
+  int acc_par = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    if (trace && threadIdx.x == 0) a.dbg[s * 8 + 0] = clock64();
+    const int t = FWD ? s : Tn - 1 - s;              // backward: t = -1 on the extra step that only produces d h_{-1}
+    const bool has_rec = FWD ? true : s > 0;
+    const int rd_slot = (s + 1) & 1;
+    __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
+    constexpr uint32_t idesc_all = ptx::make_idesc_bf16_f32(64, C::NALL, 0, 0);
+    constexpr uint32_t idesc_hi = ptx::make_idesc_bf16_f32(64, C::NC, 0, 0);
+
+    if (warp == 5) {
+      // ------------------------------- TMA producer: this CTA's K slice of the streamed operand
+      if (has_rec) {
+        ptx::fence_proxy_async_all();
+        for (int mt = 0; mt < a.m_tiles; ++mt)
+          for (int kb = 0; kb < KBS; ++kb) {
+            ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
+            const uint32_t sbase = sm.a_base + ps.stage * 2 * a.part_bytes;
+            if (ptx::elect_one()) {
+              const int kx = ((int)rank * KBS + kb) * 64;
+              ptx::mbar_expect_tx(sm.full(ps.stage), 2u * (uint32_t)a.part_bytes);
+              ptx::tma_load_2d(sbase, &tm.m[rd_slot * 2 + 0], sm.full(ps.stage), kx, mt * 64);
+              ptx::tma_load_2d(sbase + a.part_bytes, &tm.m[rd_slot * 2 + 1], sm.full(ps.stage), kx, mt * 64);
+            }
+            __syncwarp();
+            if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+          }
+      }
+    } else if (warp == 4) {
+      // ------------------------------- MMA issuer: 2 instructions per K sub-step (see mma_pass)
+      if (has_rec) {
+        for (int mt = 0; mt < a.m_tiles; ++mt) {
+          const uint32_t d = tmem_base + (uint32_t)(mt * C::NALL);
+          for (int kb = 0; kb < KBS; ++kb) {
+            ptx::mbar_wait(sm.full(ps.stage), ps.phase);
+            ptx::tc_fence_after();
+            if (trace && kb == 0 && mt == 0 && lane == 0) a.dbg[s * 8 + 1] = clock64();
+            const uint32_t sa = sm.a_base + ps.stage * 2 * a.part_bytes;
+            const uint32_t sw = sm.w_base + (uint32_t)kb * C::WT;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + a.part_bytes + k * 32, 16, 1024);
+                const uint64_t bdsc = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
+                ptx::umma_f16(d, a_hi, bdsc, idesc_all, (kb | k) ? 1u : 0u);
+                ptx::umma_f16(d, a_lo, bdsc, idesc_hi, 1u);
+              }
+              ptx::umma_commit(sm.empty(ps.stage, a.NS));
+              if (kb == KBS - 1) ptx::umma_commit(sm.acc(mt, a.NS));
+            }
+            __syncwarp();
+            if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+          }
+        }
+        if (trace && lane == 0) a.dbg[s * 8 + 2] = clock64();
+      }
+    } else if (has_rec) {
+      // ------------------------------- epilogue part 1: partial products TMEM -> registers -> shared memory
+      for (int mt = 0; mt < a.m_tiles; ++mt) {
+        ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)acc_par);
+        ptx::tc_fence_after();
+        if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
+        const int rloc = warp * 16 + (lane & 15);          // row inside the m-tile (TMEM lane 32*warp + lane%16)
+        float* prow = P + (size_t)(mt * rows_alloc + rloc) * C::PSTRIDE;
+        const bool wr_ok = lane < 16 && rloc < rows_alloc;
+#pragma unroll 1
+        for (int cb = 0; cb < C::NC; cb += 32) {
+          uint32_t r1[32], r2[32];
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + cb), r1);
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + C::NC + cb), r2);
+          ptx::tmem_ld_wait();
+          if (wr_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
+                                                       __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
+                                                       __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
+                                                       __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+    if (has_rec) {
+      acc_par ^= 1;
+      cluster_sync_all();     // every CTA of the cluster has published its partials (release/acquire, all threads)
+    }
+
+    if (warp < 4) {
+      // ------------------------------- epilogue part 2: DSMEM reduce of the owned columns + LSTM cell, 4 units/thread
+      const int items = Bd * 2;                              // (batch row, unit quad)
+      for (int it = threadIdx.x; it < items; it += 128) {
+        const int b = it >> 1, uq = it & 1, ub = u0 + uq * 4;
+        const int mt = b >> 6, rloc = b & 63;
+        const uint32_t prow = p_base + (uint32_t)((mt * rows_alloc + rloc) * C::PSTRIDE * 4);
+        if (FWD) {
+          float my[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) my[i] = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < C::CS; ++rr)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 v = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 32 + g * 8 + uq * 4) * 4), (uint32_t)rr);
+              my[g * 4 + 0] += v.x; my[g * 4 + 1] += v.y; my[g * 4 + 2] += v.z; my[g * 4 + 3] += v.w;
+            }
+          float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
+          float* g = gates_t + (int64_t)b * 4 * nh + ub;
+          float pre[16], cp[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 x0 = *(const float4*)(g + q * nh);
+            pre[q * 4 + 0] = x0.x; pre[q * 4 + 1] = x0.y; pre[q * 4 + 2] = x0.z; pre[q * 4 + 3] = x0.w;
+          }
+          const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + ub : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cp[j] = cpp ? cpp[j] : 0.f;
+          float hv[4], cv[4], act[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ig = fsigmoid(pre[j] + my[j]);
+            const float fg = fsigmoid(pre[4 + j] + my[4 + j]);
+            const float gg = ftanh(pre[8 + j] + my[8 + j]);
+            const float og = fsigmoid(pre[12 + j] + my[12 + j]);
+            const float c = fg * cp[j] + ig * gg;
+            cv[j] = c;
+            hv[j] = og * ftanh(c);
+            act[j] = ig; act[4 + j] = fg; act[8 + j] = gg; act[12 + j] = og;
+          }
+          __nv_bfloat16* d = wr + (int64_t)b * a.KP + ub;
+          store_bf16x4(d, d + (int64_t)Bd * a.KP, hv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *(float4*)(g + q * nh) = make_float4(act[q * 4], act[q * 4 + 1], act[q * 4 + 2], act[q * 4 + 3]);
+          const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
+          *(float4*)(a.c_all + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          *(float4*)(a.h_all + o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          if (a.hdrop_all) {
+            float hd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hd[j] = hv[j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + ub + j);
+            *(float4*)(a.hdrop_all + o) = make_float4(hd[0], hd[1], hd[2], hd[3]);
+          }
+        } else {
+          float rec[4] = {0.f, 0.f, 0.f, 0.f};
+          if (has_rec) {
+#pragma unroll
+            for (int rr = 0; rr < C::CS; ++rr) {
+              const float4 v = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 8 + uq * 4) * 4), (uint32_t)rr);
+              rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
+            }
+          }
+          if (t < 0) {
+            *(float4*)(a.dh_rec_out + (int64_t)b * nh + ub) = make_float4(rec[0], rec[1], rec[2], rec[3]);
+          } else {
+            const float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+            float gt[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 x0 = *(const float4*)(g + q * nh);
+              gt[q * 4 + 0] = x0.x; gt[q * 4 + 1] = x0.y; gt[q * 4 + 2] = x0.z; gt[q * 4 + 3] = x0.w;
+            }
+            const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
+            const float* cpp = t ? a.c_all + o - (int64_t)Bd * nh : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
+            float dg[16], dcn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float cc = a.c_all[o + j], cpv = cpp ? cpp[j] : 0.f, dcv = a.dc[(int64_t)b * nh + ub + j];
+              float e = 0.f;
+              if (a.dh_ext) e = a.dh_ext[o + j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + ub + j);
+              if (t == Tn - 1 && a.dh_last) e += a.dh_last[(int64_t)b * nh + ub + j];
+              const float ig = gt[j], fg = gt[4 + j], gg = gt[8 + j], og = gt[12 + j];
+              const float dh = rec[j] + e;
+              const float tc = ftanh(cc);
+              const float dct = dcv + dh * og * (1.f - tc * tc);
+              dg[j] = dct * gg * ig * (1.f - ig);
+              dg[4 + j] = dct * cpv * fg * (1.f - fg);
+              dg[8 + j] = dct * ig * (1.f - gg * gg);
+              dg[12 + j] = dh * tc * og * (1.f - og);
+              dcn[j] = dct * fg;
+            }
+            float* go = a.dgates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+            __nv_bfloat16* wb = wr + (int64_t)b * a.KP + ub;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *(float4*)(go + q * nh) = make_float4(dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]);
+              float seg[4] = {dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]};
+              store_bf16x4(wb + q * nh, wb + q * nh + (int64_t)Bd * a.KP, seg);
+            }
+            *(float4*)(a.dc + (int64_t)b * nh + ub) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+          }
+        }
+      }
+      ptx::fence_proxy_async_all();   // the operand of the next step is read by TMA (async proxy) on other SMs
+      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
+    }
+    grid_barrier(a.bar, (++epoch) * gridDim.x);   // also orders peers' DSMEM reads before the next overwrite of P
+    ptx::tc_fence_after();
+  }
+  cluster_sync_all();                              // no CTA may exit while a peer can still read its shared memory
+  if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -588,6 +899,103 @@ static int configure(LstmTcState* s) {
   return LAGVAE_OK;
 }
 
+// ---- v2 (cluster K-split) geometry / launch ---------------------------------------------------------------
+template <bool FWD>
+static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) {
+  using C = V2Cfg<FWD>;
+  static const bool off = [] { const char* e = getenv("LAGVAE_LSTM_V1"); return e && e[0] == '1'; }();
+  if (off) return false;
+  const int nh = s->nh;
+  const int K = FWD ? nh : 4 * nh;
+  if (nh % (8 * C::CS) != 0 || K % (64 * C::CS) != 0 || nh < 256) return false;
+  const int m_tiles = (int)cdiv(Bd, 64);
+  if (m_tiles * C::NALL > 512) return false;
+  const int KBS = K / 64 / C::CS;
+  const int rows_alloc = Bd >= 64 ? 64 : (int)round_up(Bd, 8);
+  const int64_t stage = 2 * (int64_t)rows_alloc * 128;
+  const int64_t wbytes = (int64_t)KBS * C::WT;
+  const int64_t pbytes = (int64_t)m_tiles * rows_alloc * C::PSTRIDE * 4;
+  int64_t n = (SMEM_LIMIT - wbytes - pbytes - MISC_BYTES) / stage;
+  n = std::min<int64_t>(n, MAX_NS);
+  n = std::min<int64_t>(n, std::max(KBS * m_tiles, 2));
+  if (n < 2) return false;
+  a->part_bytes = rows_alloc * 128;
+  a->NS = (int)n;
+  a->KP = K;
+  a->KB = K / 64;
+  a->m_tiles = m_tiles;
+  *smem = (size_t)(wbytes + pbytes + n * stage + MISC_BYTES);
+  return true;
+}
+
+template <bool FWD>
+static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, size_t smem, cudaStream_t st, bool* launched) {
+  using C = V2Cfg<FWD>;
+  static int state = 0;   // 0 unknown, 1 cooperative+cluster ok, 2 cluster only, -1 unavailable
+  *launched = false;
+  if (state < 0) return LAGVAE_OK;
+  auto kern = k_lstm_v2<FWD>;
+  if (state == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+      cudaGetLastError();
+      state = -1;
+      return LAGVAE_OK;
+    }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(s->G);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C::CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  if (state == 0) {   // all clusters must be co-resident for the grid barrier
+    int ncl = 0;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl * C::CS < s->G) {
+      cudaGetLastError();
+      state = -1;
+      return LAGVAE_OK;
+    }
+  }
+  if (state == 0 || state == 1) {
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tm);
+    if (e == cudaSuccess) {
+      state = 1;
+      *launched = true;
+      g_launches.fetch_add(1);
+      return LAGVAE_OK;
+    }
+    cudaGetLastError();
+    if (state == 1) {
+      set_error("lstm v2 launch failed: %s", cudaGetErrorString(e));
+      return LAGVAE_E_CUDA;
+    }
+  }
+  cfg.numAttrs = 1;   // cluster launch without the cooperative attribute (grid fits: checked above)
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tm);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (state == 2) {
+      set_error("lstm v2 launch failed: %s", cudaGetErrorString(e));
+      return LAGVAE_E_CUDA;
+    }
+    state = -1;
+    return LAGVAE_OK;
+  }
+  state = 2;
+  *launched = true;
+  g_launches.fetch_add(1);
+  return LAGVAE_OK;
+}
+
 static int make_maps(const LstmTcState* s, int Bd, int KP, int part_bytes, TMaps* tm) {
   for (int slot = 0; slot < 2; ++slot)
     for (int part = 0; part < 2; ++part) {
@@ -604,10 +1012,14 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_forward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
-  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPf; a.KB = s->KPf / 64;
-  a.m_tiles = (int)cdiv(Bd, 64);
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
+  const bool v2 = v2_geometry<true>(s, Bd, &a, &smem);
+  if (!v2) {
+    a.KP = s->KPf; a.KB = s->KPf / 64;
+    a.m_tiles = (int)cdiv(Bd, 64);
+    LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
+  }
   a.dbg = (g_dbg && g_dbg_words >= (size_t)Tn * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
   a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
@@ -616,6 +1028,15 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   if (s->KPf != s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPf * 2, st));
   TMaps tm;
   LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  if (v2) {
+    bool launched = false;
+    LV_TRY(v2_launch<true>(s, a, tm, smem, st, &launched));
+    if (launched) return LAGVAE_OK;
+    a.KP = s->KPf; a.KB = s->KPf / 64;   // cluster launch unavailable: v1 geometry
+    a.m_tiles = (int)cdiv(Bd, 64);
+    LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
+    LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  }
   void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
@@ -628,10 +1049,14 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_backward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
-  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn; a.KP = s->KPb; a.KB = s->KPb / 64;
-  a.m_tiles = (int)cdiv(Bd, 64);
+  a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
+  const bool v2 = v2_geometry<false>(s, Bd, &a, &smem);
+  if (!v2) {
+    a.KP = s->KPb; a.KB = s->KPb / 64;
+    a.m_tiles = (int)cdiv(Bd, 64);
+    LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
+  }
   a.dbg = (g_dbg && g_dbg_words >= (size_t)(Tn + 1) * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
   a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;
@@ -640,6 +1065,15 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   if (s->KPb != 4 * s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPb * 2, st));
   TMaps tm;
   LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  if (v2) {
+    bool launched = false;
+    LV_TRY(v2_launch<false>(s, a, tm, smem, st, &launched));
+    if (launched) return LAGVAE_OK;
+    a.KP = s->KPb; a.KB = s->KPb / 64;
+    a.m_tiles = (int)cdiv(Bd, 64);
+    LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
+    LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+  }
   void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   g_launches.fetch_add(1);
