@@ -528,9 +528,9 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank
   return v;
 }
 
-template <bool FWD>
+template <bool FWD, int CS_>
 struct V2Cfg {
-  static constexpr int CS = FWD ? 4 : 8;          // cluster size = K split
+  static constexpr int CS = CS_;                  // cluster size = K split (forward 4; backward 8, or 4 when 16 clusters of 8 do not fit)
   static constexpr int NOWN = FWD ? 32 : 8;       // result columns owned per CTA (8 units x 4 gates | 8 units)
   static constexpr int NC = CS * NOWN;            // columns of the cluster (128 | 64)
   static constexpr int NALL = 2 * NC;             // merged hi+lo weight rows = MMA N (256 | 128)
@@ -538,9 +538,9 @@ struct V2Cfg {
   static constexpr int PSTRIDE = NC + 4;          // floats per row of the partial buffer
 };
 
-template <bool FWD>
+template <bool FWD, int CS_>
 __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const __grid_constant__ TMaps tm) {
-  using C = V2Cfg<FWD>;
+  using C = V2Cfg<FWD, CS_>;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = a.nh, Bd = a.Bd, Tn = a.Tn;
@@ -573,9 +573,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
         const float* src = a.w_hh + (int64_t)(gate * nh + 32 * cl + 8 * q + uu) * nh + k0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (k0 + e < nh) ? src[e] : 0.f;
-      } else {     // row j = unit 64*cl + j ; K index = gate column k: W_hh[k, unit]
+      } else {     // row j = unit NC*cl + j ; K index = gate column k: W_hh[k, unit]
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (k0 + e < 4 * nh) ? a.w_hh[(int64_t)(k0 + e) * nh + 64 * cl + j] : 0.f;
+        for (int e = 0; e < 8; ++e) v[e] = (k0 + e < 4 * nh) ? a.w_hh[(int64_t)(k0 + e) * nh + C::NC * cl + j] : 0.f;
       }
       uint8_t* tile = gen_w + (size_t)(ck >> 3) * C::WT;
       const int c = ck & 7;
@@ -613,6 +613,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
     __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
     constexpr uint32_t idesc_all = ptx::make_idesc_bf16_f32(64, C::NALL, 0, 0);
     constexpr uint32_t idesc_hi = ptx::make_idesc_bf16_f32(64, C::NC, 0, 0);
+
+    // cell inputs of this thread's first (batch row, unit quad) item: issued now so that their L2 latency hides
+    // under the MMAs / cluster barrier (epilogue part 2 consumes them)
+    const int items = Bd * 2;
+    float pin[16], pc[4], pc2[4], pdc[4], pe[4];
+    auto load_inputs = [&](int it) {
+      const int b = it >> 1, ub = u0 + (it & 1) * 4;
+      if (FWD) {
+        const float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 x0 = *(const float4*)(g + q * nh);
+          pin[q * 4 + 0] = x0.x; pin[q * 4 + 1] = x0.y; pin[q * 4 + 2] = x0.z; pin[q * 4 + 3] = x0.w;
+        }
+        const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + ub : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pc[j] = cpp ? cpp[j] : 0.f;
+      } else if (t >= 0) {
+        const float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 x0 = *(const float4*)(g + q * nh);
+          pin[q * 4 + 0] = x0.x; pin[q * 4 + 1] = x0.y; pin[q * 4 + 2] = x0.z; pin[q * 4 + 3] = x0.w;
+        }
+        const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
+        const float* cpp = t ? a.c_all + o - (int64_t)Bd * nh : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pc[j] = a.c_all[o + j];
+          pc2[j] = cpp ? cpp[j] : 0.f;
+          pdc[j] = a.dc[(int64_t)b * nh + ub + j];
+          float e = 0.f;
+          if (a.dh_ext) e = a.dh_ext[o + j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + ub + j);
+          if (t == Tn - 1 && a.dh_last) e += a.dh_last[(int64_t)b * nh + ub + j];
+          pe[j] = e;
+        }
+      }
+    };
+    if (warp < 4 && (int)threadIdx.x < items) load_inputs((int)threadIdx.x);
 
     if (warp == 5) {
       // ------------------------------- TMA producer: this CTA's K slice of the streamed operand
@@ -695,8 +734,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
 
     if (warp < 4) {
       // ------------------------------- epilogue part 2: DSMEM reduce of the owned columns + LSTM cell, 4 units/thread
-      const int items = Bd * 2;                              // (batch row, unit quad)
-      for (int it = threadIdx.x; it < items; it += 128) {
+      for (int it = threadIdx.x; it < items; it += 128) {     // item = (batch row, unit quad)
+        if (it != (int)threadIdx.x) load_inputs(it);
         const int b = it >> 1, uq = it & 1, ub = u0 + uq * 4;
         const int mt = b >> 6, rloc = b & 63;
         const uint32_t prow = p_base + (uint32_t)((mt * rows_alloc + rloc) * C::PSTRIDE * 4);
@@ -711,17 +750,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
               const float4 v = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 32 + g * 8 + uq * 4) * 4), (uint32_t)rr);
               my[g * 4 + 0] += v.x; my[g * 4 + 1] += v.y; my[g * 4 + 2] += v.z; my[g * 4 + 3] += v.w;
             }
-          float* gates_t = a.gates + (int64_t)t * Bd * 4 * nh;
-          float* g = gates_t + (int64_t)b * 4 * nh + ub;
-          float pre[16], cp[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 x0 = *(const float4*)(g + q * nh);
-            pre[q * 4 + 0] = x0.x; pre[q * 4 + 1] = x0.y; pre[q * 4 + 2] = x0.z; pre[q * 4 + 3] = x0.w;
-          }
-          const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + ub : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cp[j] = cpp ? cpp[j] : 0.f;
+          float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+          const float (&pre)[16] = pin;
+          const float (&cp)[4] = pc;
           float hv[4], cv[4], act[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -760,22 +791,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
           if (t < 0) {
             *(float4*)(a.dh_rec_out + (int64_t)b * nh + ub) = make_float4(rec[0], rec[1], rec[2], rec[3]);
           } else {
-            const float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
-            float gt[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 x0 = *(const float4*)(g + q * nh);
-              gt[q * 4 + 0] = x0.x; gt[q * 4 + 1] = x0.y; gt[q * 4 + 2] = x0.z; gt[q * 4 + 3] = x0.w;
-            }
+            const float (&gt)[16] = pin;
             const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
-            const float* cpp = t ? a.c_all + o - (int64_t)Bd * nh : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
+            (void)o;
             float dg[16], dcn[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float cc = a.c_all[o + j], cpv = cpp ? cpp[j] : 0.f, dcv = a.dc[(int64_t)b * nh + ub + j];
-              float e = 0.f;
-              if (a.dh_ext) e = a.dh_ext[o + j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + ub + j);
-              if (t == Tn - 1 && a.dh_last) e += a.dh_last[(int64_t)b * nh + ub + j];
+              const float cc = pc[j], cpv = pc2[j], dcv = pdc[j], e = pe[j];
               const float ig = gt[j], fg = gt[4 + j], gg = gt[8 + j], og = gt[12 + j];
               const float dh = rec[j] + e;
               const float tc = ftanh(cc);
@@ -900,9 +922,9 @@ static int configure(LstmTcState* s) {
 }
 
 // ---- v2 (cluster K-split) geometry / launch ---------------------------------------------------------------
-template <bool FWD>
+template <bool FWD, int CS_>
 static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) {
-  using C = V2Cfg<FWD>;
+  using C = V2Cfg<FWD, CS_>;
   static const bool off = [] { const char* e = getenv("LAGVAE_LSTM_V1"); return e && e[0] == '1'; }();
   if (off) return false;
   const int nh = s->nh;
@@ -928,13 +950,13 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
   return true;
 }
 
-template <bool FWD>
+template <bool FWD, int CS_>
 static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, size_t smem, cudaStream_t st, bool* launched) {
-  using C = V2Cfg<FWD>;
+  using C = V2Cfg<FWD, CS_>;
   static int state = 0;   // 0 unknown, 1 cooperative+cluster ok, 2 cluster only, -1 unavailable
   *launched = false;
   if (state < 0) return LAGVAE_OK;
-  auto kern = k_lstm_v2<FWD>;
+  auto kern = k_lstm_v2<FWD, CS_>;
   if (state == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
       cudaGetLastError();
@@ -1014,7 +1036,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   RecArgs a{};
   a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  const bool v2 = v2_geometry<true>(s, Bd, &a, &smem);
+  const bool v2 = v2_geometry<true, 4>(s, Bd, &a, &smem);
   if (!v2) {
     a.KP = s->KPf; a.KB = s->KPf / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
@@ -1030,7 +1052,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
   if (v2) {
     bool launched = false;
-    LV_TRY(v2_launch<true>(s, a, tm, smem, st, &launched));
+    LV_TRY((v2_launch<true, 4>(s, a, tm, smem, st, &launched)));
     if (launched) return LAGVAE_OK;
     a.KP = s->KPf; a.KB = s->KPf / 64;   // cluster launch unavailable: v1 geometry
     a.m_tiles = (int)cdiv(Bd, 64);
@@ -1051,7 +1073,13 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   RecArgs a{};
   a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  const bool v2 = v2_geometry<false>(s, Bd, &a, &smem);
+  static int cs_ok = 8;   // 16 clusters of 8 CTAs do not fit on every B200 (GPC sizes): fall back to clusters of 4
+  bool v2 = cs_ok == 8 && v2_geometry<false, 8>(s, Bd, &a, &smem);
+  int v2cs = v2 ? 8 : 0;
+  if (!v2 && cs_ok >= 4) {
+    v2 = v2_geometry<false, 4>(s, Bd, &a, &smem);
+    v2cs = v2 ? 4 : 0;
+  }
   if (!v2) {
     a.KP = s->KPb; a.KB = s->KPb / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
@@ -1067,8 +1095,20 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
   if (v2) {
     bool launched = false;
-    LV_TRY(v2_launch<false>(s, a, tm, smem, st, &launched));
-    if (launched) return LAGVAE_OK;
+    if (v2cs == 8) {
+      LV_TRY((v2_launch<false, 8>(s, a, tm, smem, st, &launched)));
+      if (launched) return LAGVAE_OK;
+      cs_ok = 4;
+      if (v2_geometry<false, 4>(s, Bd, &a, &smem)) {
+        LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+        LV_TRY((v2_launch<false, 4>(s, a, tm, smem, st, &launched)));
+        if (launched) return LAGVAE_OK;
+      }
+    } else {
+      LV_TRY((v2_launch<false, 4>(s, a, tm, smem, st, &launched)));
+      if (launched) return LAGVAE_OK;
+    }
+    cs_ok = 0;
     a.KP = s->KPb; a.KB = s->KPb / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
     LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
