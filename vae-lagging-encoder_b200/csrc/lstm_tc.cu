@@ -556,6 +556,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
   sm.bar_base = p_base + (uint32_t)(a.m_tiles * rows_alloc * C::PSTRIDE * 4);
   uint8_t* gen_w = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   float* P = (float*)(smem_raw + (p_base - ptx::smem_u32(smem_raw)));
+  // "stacked M" (Bd <= 32): the ring stage is [hi rows ; lo rows] contiguously, so ONE M=64 MMA whose A descriptor
+  // starts at the hi part covers both operand parts: D rows [0,ra) = A_hi·[W_hi;W_lo], rows [ra,2ra) = A_lo·[W_hi;W_lo];
+  // the epilogue adds D[b,0:NC] + D[b,NC:2NC] + D[ra+b,0:NC].  Halves the tcgen05.mma count per time step.
+  const bool stack = a.m_tiles == 1 && 2 * rows_alloc <= 64;
   const int tmem_need = a.m_tiles * C::NALL;
   const int tmem_cols = tmem_need <= 128 ? 128 : (tmem_need <= 256 ? 256 : 512);
 
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
                 const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + a.part_bytes + k * 32, 16, 1024);
                 const uint64_t bdsc = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
                 ptx::umma_f16(d, a_hi, bdsc, idesc_all, (kb | k) ? 1u : 0u);
-                ptx::umma_f16(d, a_lo, bdsc, idesc_hi, 1u);
+                if (!stack) ptx::umma_f16(d, a_lo, bdsc, idesc_hi, 1u);
               }
               ptx::umma_commit(sm.empty(ps.stage, a.NS));
               if (kb == KBS - 1) ptx::umma_commit(sm.acc(mt, a.NS));
@@ -706,22 +710,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
         ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)acc_par);
         ptx::tc_fence_after();
         if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
-        const int rloc = warp * 16 + (lane & 15);          // row inside the m-tile (TMEM lane 32*warp + lane%16)
-        float* prow = P + (size_t)(mt * rows_alloc + rloc) * C::PSTRIDE;
-        const bool wr_ok = lane < 16 && rloc < rows_alloc;
+        const int rloc = warp * 16 + (lane & 15);          // MMA row inside the m-tile (TMEM lane 32*warp + lane%16)
+        if (!stack) {
+          float* prow = P + (size_t)(mt * rows_alloc + rloc) * C::PSTRIDE;
+          const bool wr_ok = lane < 16 && rloc < rows_alloc;
 #pragma unroll 1
-        for (int cb = 0; cb < C::NC; cb += 32) {
-          uint32_t r1[32], r2[32];
-          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + cb), r1);
-          ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + C::NC + cb), r2);
-          ptx::tmem_ld_wait();
-          if (wr_ok) {
+          for (int cb = 0; cb < C::NC; cb += 32) {
+            uint32_t r1[32], r2[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + cb), r1);
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + C::NC + cb), r2);
+            ptx::tmem_ld_wait();
+            if (wr_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
-                                                       __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
-                                                       __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
-                                                       __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
+              for (int j = 0; j < 32; j += 4)
+                *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
+                                                         __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
+                                                         __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
+                                                         __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
+            }
+          }
+        } else {
+          // phase 1: hi rows (MMA row r < ra = batch row r): P[r] = D[r,0:NC] + D[r,NC:2NC]
+          const bool hi_row = lane < 16 && rloc < rows_alloc;
+          const bool lo_row = lane < 16 && rloc >= rows_alloc && rloc < 2 * rows_alloc;
+          float* prow = P + (size_t)(hi_row ? rloc : (lo_row ? rloc - rows_alloc : 0)) * C::PSTRIDE;
+          const bool any_hi = warp * 16 < rows_alloc, any_lo = warp * 16 + 15 >= rows_alloc && warp * 16 < 2 * rows_alloc;
+          if (any_hi) {
+#pragma unroll 1
+            for (int cb = 0; cb < C::NC; cb += 32) {
+              uint32_t r1[32], r2[32];
+              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r1);
+              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::NC + cb), r2);
+              ptx::tmem_ld_wait();
+              if (hi_row) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
+                                                           __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
+                                                           __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
+                                                           __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps: phase-1 rows are in P
+          // phase 2: lo rows (MMA row ra + b): P[b] += D[ra+b, 0:NC]
+          if (any_lo) {
+#pragma unroll 1
+            for (int cb = 0; cb < C::NC; cb += 32) {
+              uint32_t r1[32];
+              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r1);
+              ptx::tmem_ld_wait();
+              if (lo_row) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 v = *(float4*)(prow + cb + j);
+                  v.x += __uint_as_float(r1[j]); v.y += __uint_as_float(r1[j + 1]);
+                  v.z += __uint_as_float(r1[j + 2]); v.w += __uint_as_float(r1[j + 3]);
+                  *(float4*)(prow + cb + j) = v;
+                }
+              }
+            }
           }
         }
       }
