@@ -106,9 +106,15 @@ int lagvae_text_loss_forward(lagvae_text_plan* plan, const lagvae_text_params* p
  * gradients of the three outputs, fp32 [B], any may be NULL (= zeros).  `grads` receives the 13
  * gradients (overwritten, not accumulated); decoder.embed.weight row V-1 gets zeros
  * (padding_idx=-1, dec_lstm.py:28). */
+#define LAGVAE_BWD_DEFAULT 0u
+/* The decoder WEIGHT gradients (pred_linear, decoder lstm weight_ih/hh) feed only the clip norm in the aggressive
+ * loop (text.py:385; the decoder is not stepped, text.py:387): compute them with ONE bf16 pass instead of three
+ * (norm error ~1e-5).  Everything that reaches the encoder update stays fp32-grade. */
+#define LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY 1u
 int lagvae_text_loss_backward(lagvae_text_plan* plan, const lagvae_text_params* params,
                               const int64_t* x, const float* g_loss, const float* g_rec,
-                              const float* g_kl, const lagvae_text_params* grads, void* stream);
+                              const float* g_kl, const lagvae_text_params* grads, uint32_t flags,
+                              void* stream);
 
 /* Encoder forward only: enc_lstm.py:47-64 (VAE.encode_stats vae.py:33-40). */
 int lagvae_text_encode_stats(lagvae_text_plan* plan, const lagvae_text_params* params,

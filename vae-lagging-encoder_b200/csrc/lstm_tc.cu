@@ -572,9 +572,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
       if (FWD) { j = id / nchunk; ck = id % nchunk; } else { j = id % C::NC; ck = id / C::NC; }
       const int k0 = kslice0 + ck * 8;
       float v[8];
-      if (FWD) {   // column j = q*32 + gate*8 + uu  <->  W_hh row gate*nh + 32*cl + 8q + uu ; K index = hidden unit
+      if (FWD) {   // column j = q*32 + gate*8 + uu  <->  W_hh row gate*nh + (8 CS) cl + 8q + uu ; K index = hidden unit
         const int q = j >> 5, gate = (j >> 3) & 3, uu = j & 7;
-        const float* src = a.w_hh + (int64_t)(gate * nh + 32 * cl + 8 * q + uu) * nh + k0;
+        const float* src = a.w_hh + (int64_t)(gate * nh + 8 * C::CS * cl + 8 * q + uu) * nh + k0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (k0 + e < nh) ? src[e] : 0.f;
       } else {     // row j = unit NC*cl + j ; K index = gate column k: W_hh[k, unit]
@@ -788,16 +788,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
         const int mt = b >> 6, rloc = b & 63;
         const uint32_t prow = p_base + (uint32_t)((mt * rows_alloc + rloc) * C::PSTRIDE * 4);
         if (FWD) {
-          float my[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) my[i] = 0.f;
+          // issue every distributed-shared-memory load before consuming any (each is ~200+ cycles of latency)
+          float4 pv[C::CS * 4];
 #pragma unroll
           for (int rr = 0; rr < C::CS; ++rr)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 v = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 32 + g * 8 + uq * 4) * 4), (uint32_t)rr);
-              my[g * 4 + 0] += v.x; my[g * 4 + 1] += v.y; my[g * 4 + 2] += v.z; my[g * 4 + 3] += v.w;
+            for (int g = 0; g < 4; ++g)
+              pv[rr * 4 + g] = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 32 + g * 8 + uq * 4) * 4), (uint32_t)rr);
+          float my[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float4 acc4 = pv[g];
+#pragma unroll
+            for (int rr = 1; rr < C::CS; ++rr) {
+              acc4.x += pv[rr * 4 + g].x; acc4.y += pv[rr * 4 + g].y; acc4.z += pv[rr * 4 + g].z; acc4.w += pv[rr * 4 + g].w;
             }
+            my[g * 4 + 0] = acc4.x; my[g * 4 + 1] = acc4.y; my[g * 4 + 2] = acc4.z; my[g * 4 + 3] = acc4.w;
+          }
           float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
           const float (&pre)[16] = pin;
           const float (&cp)[4] = pc;
@@ -830,11 +837,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
         } else {
           float rec[4] = {0.f, 0.f, 0.f, 0.f};
           if (has_rec) {
+            float4 pv[C::CS];
 #pragma unroll
-            for (int rr = 0; rr < C::CS; ++rr) {
-              const float4 v = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 8 + uq * 4) * 4), (uint32_t)rr);
-              rec[0] += v.x; rec[1] += v.y; rec[2] += v.z; rec[3] += v.w;
-            }
+            for (int rr = 0; rr < C::CS; ++rr)
+              pv[rr] = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 8 + uq * 4) * 4), (uint32_t)rr);
+#pragma unroll
+            for (int rr = 0; rr < C::CS; ++rr) { rec[0] += pv[rr].x; rec[1] += pv[rr].y; rec[2] += pv[rr].z; rec[3] += pv[rr].w; }
           }
           if (t < 0) {
             *(float4*)(a.dh_rec_out + (int64_t)b * nh + ub) = make_float4(rec[0], rec[1], rec[2], rec[3]);
@@ -1084,7 +1092,14 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   RecArgs a{};
   a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  const bool v2 = v2_geometry<true, 4>(s, Bd, &a, &smem);
+  // cluster of 2 when the stacked-M mode applies (Bd <= 32: same MMA time as a cluster of 4, half the partial-sum
+  // traffic), cluster of 4 otherwise
+  static const int force_cs = [] { const char* e = getenv("LAGVAE_LSTM_FWD_CS"); return e ? atoi(e) : 0; }();
+  const int want_cs = force_cs ? force_cs : (Bd <= 32 ? 2 : 4);
+  bool v2 = false;
+  int v2cs = 0;
+  if (want_cs == 2) { v2 = v2_geometry<true, 2>(s, Bd, &a, &smem); v2cs = v2 ? 2 : 0; }
+  if (!v2) { v2 = v2_geometry<true, 4>(s, Bd, &a, &smem); v2cs = v2 ? 4 : 0; }
   if (!v2) {
     a.KP = s->KPf; a.KB = s->KPf / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
@@ -1100,7 +1115,15 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
   if (v2) {
     bool launched = false;
-    LV_TRY((v2_launch<true, 4>(s, a, tm, smem, st, &launched)));
+    if (v2cs == 2) {
+      LV_TRY((v2_launch<true, 2>(s, a, tm, smem, st, &launched)));
+      if (!launched && v2_geometry<true, 4>(s, Bd, &a, &smem)) {
+        LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
+        LV_TRY((v2_launch<true, 4>(s, a, tm, smem, st, &launched)));
+      }
+    } else {
+      LV_TRY((v2_launch<true, 4>(s, a, tm, smem, st, &launched)));
+    }
     if (launched) return LAGVAE_OK;
     a.KP = s->KPf; a.KB = s->KPf / 64;   // cluster launch unavailable: v1 geometry
     a.m_tiles = (int)cdiv(Bd, 64);

@@ -500,9 +500,10 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* P, const lagvae_text_params*
 
 int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
                               const float* g_loss, const float* g_rec, const float* g_kl,
-                              const lagvae_text_params* gr, void* stream) {
+                              const lagvae_text_params* gr, uint32_t flags, void* stream) {
   LV_CHECK_ARG(P && w && x && gr, "loss_backward: null argument");
   LV_CHECK_ARG(P->have_forward, "loss_backward: no forward stash on this plan");
+  P->dec_wgrad_passes = (flags & LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY) ? 1 : 3;
   cudaStream_t st = (cudaStream_t)stream;
   const lagvae_text_dims& d = P->d;
   const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td, Te = P->Te;
@@ -653,10 +654,7 @@ int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, con
   LV_TRY(fill(P->dc0t, 1.f / (float)d.B, d.B, st));
   // decoder WEIGHT gradients are never applied in this loop (text.py:387 steps the encoder only); they enter
   // the update through the clip norm alone (text.py:385), for which one bf16 pass is ample (norm error ~1e-5)
-  P->dec_wgrad_passes = 1;
-  const int rb = lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, stream);
-  P->dec_wgrad_passes = 3;
-  LV_TRY(rb);
+  LV_TRY(lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY, stream));
   // text.py:385 clip over all 13 grads; :387 encoder-only SGD step
   LV_TRY(clip_sgd_step(w->p, g.p, counts, LAGVAE_TEXT_NPARAM, 6, max_norm, lr, 0, out_scalars + 3,
                        P->clip_scratch, st));

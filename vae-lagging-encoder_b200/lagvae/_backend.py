@@ -14,6 +14,7 @@ OK, E_ARG, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 ABI_VERSION = 1
 NPARAM = 13
 PLAN_DEFAULT, PLAN_FORCE_SIMT, PLAN_INFERENCE = 0, 1, 2
+BWD_DEFAULT, BWD_DECODER_WGRAD_NORM_ONLY = 0, 1
 
 
 class LagvaeError(RuntimeError):
@@ -47,7 +48,7 @@ PROTOTYPES = {
     "lagvae_text_loss_forward": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout),
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lagvae_text_loss_backward": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _vp, _vp,
-                                       C.POINTER(TextParams), _vp]),
+                                       C.POINTER(TextParams), _u32, _vp]),
     "lagvae_text_encode_stats": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _vp, _vp]),
     "lagvae_text_reconstruct_error": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, C.POINTER(Dropout), _vp, _vp]),
     "lagvae_clip_sgd_step": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _f, _f, _i,

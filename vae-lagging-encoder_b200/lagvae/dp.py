@@ -71,7 +71,8 @@ class EngineBackend:
         B = x.shape[0]
         loss, _, _ = eng.loss_forward(params, x, self.eps_fn(B), self.kl_weight, self.drop_fn())
         gl = torch.full((B,), g_scale, dtype=torch.float32, device=x.device)
-        eng.loss_backward(params, x, gl, None, None, grads_out=self._views)
+        # aggressive loop: decoder weights are not stepped, their gradients only enter the clip norm
+        eng.loss_backward(params, x, gl, None, None, grads_out=self._views, decoder_wgrad_norm_only=True)
         return loss
 
     def clip_sgd(self, params, flat_grads, max_norm, lr):

@@ -170,7 +170,8 @@ class TextEngine:
             return out[0], out[1], out[2], mu, logvar, z
         return out[0], out[1], out[2]
 
-    def loss_backward(self, params, x, g_loss, g_rec, g_kl, generation=None, grads_out=None) -> List[torch.Tensor]:
+    def loss_backward(self, params, x, g_loss, g_rec, g_kl, generation=None, grads_out=None,
+                      decoder_wgrad_norm_only=False) -> List[torch.Tensor]:
         if generation is not None and generation != self.generation:
             raise be.LagvaeError("backward called after another forward on the same engine: the stash of "
                                  "this loss has been overwritten (one live VAE.loss graph per model)")
@@ -183,7 +184,9 @@ class TextEngine:
         tg = self._params(grads, "grads")
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_loss_backward(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(gl),
-                                                        be.ptr(gr), be.ptr(gk), C.byref(tg), _stream()),
+                                                        be.ptr(gr), be.ptr(gk), C.byref(tg),
+                                                        be.BWD_DECODER_WGRAD_NORM_ONLY if decoder_wgrad_norm_only else be.BWD_DEFAULT,
+                                                        _stream()),
                      "lagvae_text_loss_backward")
         return grads
 
