@@ -201,6 +201,53 @@ void lagvae_debug_trace_buffer(void* dev_u64, size_t words);
 int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Image path (ResNetEncoderV2 enc_resnet_v2.py:93-126, PixelCNNDecoderV2 dec_pixelcnn_v2.py:123-195).
+ * Activations are NHWC fp32: a [B,H,W,C] tensor is the matrix [B*H*W rows, C]; a convolution is
+ * im2col (identity for 1x1 stride 1) + lagvae_gemm_auto against the weight reshaped to [Cout, kh*kw*Cin]
+ * (tap-major, channel-minor); its backward is two more GEMMs + col2im.
+ * ------------------------------------------------------------------------------------------- */
+/* nn.Conv2d patch gather / its adjoint (replaces cuDNN implicit-GEMM convolution).  Output spatial size
+ * Ho = (H + 2 pad - kh)/stride + 1.  col [B*Ho*Wo, kh*kw*C]; dx [B,H,W,C] is overwritten. */
+int lagvae_im2col(const float* x, int B, int H, int W, int C, int kh, int kw, int stride, int pad, float* col,
+                  void* stream);
+int lagvae_col2im(const float* dcol, int B, int H, int W, int C, int kh, int kw, int stride, int pad, float* dx,
+                  void* stream);
+/* nn.BatchNorm2d in train(): batch statistics over the R rows (biased variance), running stats updated in place
+ * with the unbiased variance (momentum 0.1 default); scratch: device, >= 16*C bytes.  Backward returns dx, dgamma,
+ * dbeta. */
+int lagvae_bn_train_fwd(const float* x, int64_t R, int C, const float* gamma, const float* beta, float eps,
+                        float momentum, float* y, float* save_mean, float* save_invstd, float* running_mean,
+                        float* running_var, void* scratch, void* stream);
+int lagvae_bn_train_bwd(const float* x, const float* dy, int64_t R, int C, const float* gamma, const float* save_mean,
+                        const float* save_invstd, float* dx, float* dgamma, float* dbeta, void* scratch, void* stream);
+/* eval()-mode BatchNorm: y = (x - mean) * invstd * gamma + beta with caller-provided per-channel statistics. */
+int lagvae_bn_apply(const float* x, int64_t R, int C, const float* mean, const float* invstd, const float* gamma,
+                    const float* beta, float* y, void* stream);
+/* nn.ELU(alpha=1) of (a + b) (b may be NULL: plain ELU; with b: the residual add of ResNetBlock / PixelCNNBlock fused
+ * in); backward from the OUTPUT y. */
+int lagvae_elu_fwd(const float* a, const float* b_or_null, float* y, int64_t n, void* stream);
+int lagvae_elu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+int lagvae_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* nn.Sigmoid + the Bernoulli NLL of dec_pixelcnn_v2.py:172-195 (eps = 1e-12 inside both logs): logits [B*ns, P],
+ * x [B, P] -> nll [B*ns]; backward: dlogits = g[row] * d nll / d logit. */
+int lagvae_bernoulli_nll_fwd(const float* logits, const float* x, int B, int ns, int P, float* nll, void* stream);
+int lagvae_bernoulli_nll_bwd(const float* logits, const float* x, const float* g, int B, int ns, int P, float* dlogits,
+                             void* stream);
+/* Reparameterise + analytic KL on given (mu, logvar) [B,nz] (encoder.py:55,72-79): z [B,ns,nz], kl [B]; backward
+ * writes dml [B, 2nz] = (dmu | dlogvar) from dz (may be NULL) and the upstream gradient of KL (may be NULL). */
+int lagvae_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, int B, int nz, int ns, float* z,
+                          float* kl, void* stream);
+int lagvae_reparam_kl_bwd(const float* dz, const float* eps, const float* mu, const float* logvar, const float* g_kl,
+                          int B, int nz, int ns, float* dml, void* stream);
+/* GEMM dispatcher used by the image layers and nn.Linear: C[M,N] = alpha * Σ_k A(m,k) B(n,k) + beta C + bias_n with
+ * strided fp32 operands; stages split-bf16 copies into `scratch` and runs lagvae_gemm_tc (3 passes) when the problem
+ * is tensor-core sized, else lagvae_gemm_f32. */
+size_t lagvae_gemm_auto_scratch_bytes(int M, int N, int K);
+int lagvae_gemm_auto(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C,
+                     int64_t ldc, int M, int N, int K, float alpha, float beta, const float* bias_n, void* scratch,
+                     size_t scratch_bytes, void* stream);
+
 /* materialise the Philox dropout keep-mask the kernels would use (tests feed it to the oracle) */
 int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep,
                         void* stream);

@@ -1,0 +1,94 @@
+"""Parity of the image path (ResNetEncoderV2 + PixelCNNDecoderV2, training-mode BatchNorm)
+against the image oracle and the fixtures written from the unmodified reference."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import image_oracle as IO
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(nz):
+    import modules
+    a = types.SimpleNamespace(nz=nz, latent_feature_map=4, device=torch.device("cuda"))
+    vae = modules.VAE(modules.ResNetEncoderV2(a), modules.PixelCNNDecoderV2(a), a).to("cuda")
+    p = IO.init_image_params(nz, seed=0)
+    assert list(vae.state_dict().keys()) == list(p.keys())          # reference state_dict compatibility
+    vae.load_state_dict(p)
+    return vae, p
+
+
+@pytest.mark.parametrize("name", ["omniglot_b8", "omniglot_b3_ns2"])
+def test_image_loss_and_grads_vs_reference_golden(golden, name):
+    from modules.image import _ReparamKLFn
+    g = golden(name)
+    B, nz, ns = [int(v) for v in g["meta"]]
+    vae, p = _build(nz)
+    vae.train()
+    x = torch.from_numpy(g["x"]).cuda()
+    eps = torch.from_numpy(g["eps"]).cuda()
+    klw = float(g["kl_weight"])
+    mu, logvar = vae.encoder(x)
+    z, kl = _ReparamKLFn.apply(mu, logvar, eps)
+    rec = vae.decoder.reconstruct_error(x, z).mean(dim=1)
+    loss = rec + klw * kl
+    assert_close(loss, g["loss"], 1e-4, "loss")
+    assert_close(rec, g["rec"], 1e-4, "rec")
+    assert_close(kl, g["kl"], 1e-4, "kl", floor=1e-2)
+    loss.mean(dim=-1).backward()
+    bad, tot = [], 0.0
+    grads = dict(vae.named_parameters())
+    for n in [str(s) for s in g["names"]]:
+        gr = grads[n].grad
+        nrm = float(gr.double().norm())
+        tot += nrm * nrm
+        want = float(g["gnorm." + n])
+        sl = gr.reshape(-1)[:: max(1, gr.numel() // 32)][:32].cpu().double()
+        ws = torch.from_numpy(g["gslice." + n]).double()
+        serr = float((sl - ws).abs().max()) / max(float(gr.abs().max()) * 0.05, float(ws.abs().max()), 1e-12)
+        if abs(nrm - want) > 3e-3 * max(want, 1e-6) or serr > 1e-2:
+            bad.append("%s: norm %.6g want %.6g, slice err %.2e" % (n, nrm, want, serr))
+    assert not bad, "\n".join(bad)
+    assert abs(tot ** 0.5 - float(g["grad_norm"])) <= 2e-3 * float(g["grad_norm"])
+    # running statistics were updated exactly once, with the unbiased variance
+    sd = vae.state_dict()
+    for k in g:
+        if k.startswith("post."):
+            assert_close(sd[k[5:]], g[k], 1e-4, k, floor=1e-3)
+    # masked taps are zeroed in the weights by the forward (dec_pixelcnn_v2.py:29)
+    w, m = sd["decoder.main.0.main.1.main.3.weight"], sd["decoder.main.0.main.1.main.3.mask"]
+    assert float((w * (1 - m)).abs().max()) == 0.0
+
+
+def test_image_module_api_inner_step_vs_oracle():
+    """The statement sequence of image.py:300-314 (Adam encoder step) against the oracle on the same draws."""
+    B, nz = 4, 16
+    vae, p = _build(nz)
+    vae.train()
+    x = IO.make_image_batch(B, seed=5)
+    torch.manual_seed(3)
+    eps = torch.empty(B, 1, nz, device="cuda").normal_()
+    leaves = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k and "mask" not in k) for k, v in p.items()}
+    o_loss, o_rec, o_kl = IO.vae_loss(leaves, x, 0.3, eps.cpu())
+    o_loss.mean().backward()
+    enc_opt = torch.optim.Adam(vae.encoder.parameters(), lr=0.001)
+    dec_opt = torch.optim.Adam(vae.decoder.parameters(), lr=0.001)
+    enc_opt.zero_grad()
+    dec_opt.zero_grad()
+    torch.manual_seed(3)
+    loss, loss_rc, loss_kl = vae.loss(x.cuda(), 0.3, nsamples=1)
+    s = loss.sum().item()
+    loss.mean(dim=-1).backward()
+    torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0)
+    enc_opt.step()
+    assert abs(s - float(o_loss.sum())) <= 1e-4 * abs(float(o_loss.sum()))
+    assert_close(loss_kl, o_kl.detach(), 1e-4, "kl", floor=1e-2)
+    with torch.no_grad():
+        vae.eval()
+        l2, _, _ = vae.loss(x.cuda(), 1.0)
+        assert bool(torch.isfinite(l2).all()) and not l2.requires_grad
+        assert isinstance(vae.calc_mi_q(x.cuda()), float)

@@ -62,6 +62,20 @@ PROTOTYPES = {
     "lagvae_lstm_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _vp, _i,
                                   _vp, _sz, _vp]),
     "lagvae_debug_trace_buffer": (None, [_vp, _sz]),
+    "lagvae_im2col": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lagvae_col2im": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lagvae_bn_train_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_bn_train_bwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_bn_apply": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_elu_fwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lagvae_elu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lagvae_add": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lagvae_bernoulli_nll_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "lagvae_bernoulli_nll_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "lagvae_reparam_kl_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lagvae_reparam_kl_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "lagvae_gemm_auto_scratch_bytes": (_sz, [_i, _i, _i]),
+    "lagvae_gemm_auto": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "lagvae_gemm_f32": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp]),
     "lagvae_gemm_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _f, _f,
                             _vp, _vp, _i, _vp, _vp]),

@@ -4,4 +4,5 @@ parent (`vae-lagging-encoder_b200/`) precedes the reference on sys.path, so the 
 text.py / toy.py run unmodified on the B200 kernels.  See INTEGRATION.md."""
 from .utils import generate_grid, log_sum_exp  # noqa: F401
 from .text import DecoderBase, GaussianEncoderBase, LSTMDecoder, LSTMEncoder  # noqa: F401
+from .image import MaskedConv2d, PixelCNNDecoderV2, ResNetEncoderV2  # noqa: F401
 from .vae import VAE  # noqa: F401
