@@ -183,6 +183,45 @@ def time_vocab_gemm(eng, reps=5):
     return 2.0 * M * N * K, ms
 
 
+def time_lstm_kernels(reps=3):
+    """The dominant kernels of the step: the persistent tcgen05 LSTM recurrences (one launch = all T time steps),
+    timed alone with CUDA events on the launching stream at the Yahoo recurrence shape."""
+    import ctypes as C
+    import lagvae._backend as be
+    c = CFG
+    nh, Bd, Tn = c["nh"], c["B"], c["T"]
+    w_hh = (torch.rand(4 * nh, nh, device="cuda") * 2 - 1) * (1.0 / nh ** 0.5)
+    pre = torch.randn(Tn * Bd, 4 * nh, device="cuda")
+    ws = torch.zeros(int(be.lib().lagvae_lstm_workspace_bytes(nh, Bd)), dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    drop = be.Dropout()
+    gates = pre.clone()
+    c_all, h_all = torch.zeros(Tn * Bd, nh, device="cuda"), torch.zeros(Tn * Bd, nh, device="cuda")
+    dh = torch.randn(Tn * Bd, nh, device="cuda") * 0.01
+    dc, dhr, dg = torch.zeros(Bd, nh, device="cuda"), torch.zeros(Bd, nh, device="cuda"), torch.zeros(Tn * Bd, 4 * nh, device="cuda")
+    fwd = lambda: be.check(be.lib().lagvae_lstm_forward(1, nh, Tn, Bd, be.ptr(w_hh), None, None, be.ptr(gates), be.ptr(c_all),
+                                                        be.ptr(h_all), None, C.byref(drop), be.ptr(ws), ws.numel(), st))
+    bwd = lambda: be.check(be.lib().lagvae_lstm_backward(1, nh, Tn, Bd, be.ptr(w_hh), None, be.ptr(gates), be.ptr(c_all), be.ptr(dh),
+                                                         None, C.byref(drop), be.ptr(dc), be.ptr(dhr), be.ptr(dg), 1, be.ptr(ws), ws.numel(), st))
+    out = {}
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        gates.copy_(pre) if name == "fwd" else None
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            if name == "fwd":
+                gates.copy_(pre)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        out[name] = float(np.median(ms))
+    return out, 2.0 * Bd * nh * 4 * nh * Tn
+
+
 def run_ours(args, rank, world, local_rank):
     import lagvae
     import lagging_oracle as O
@@ -325,12 +364,23 @@ def run_ours(args, rank, world, local_rank):
     peaks, peak_src = measured_peaks()
     F = flops_step(B, T, V, c["ni"], c["nh"], c["nz"])
     gflop, gms = time_vocab_gemm(eng)
-    roof = {"bound": "tensor", "kernel": "k_gemm_tc<K-major,K-major> vocab projection 6368x20001x1024 (split-bf16, 3 MMA passes)",
-            "achieved": gflop / (gms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": gflop / (gms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
-            "peak_source": peak_src + " bf16 burst (kernel timed alone); algorithmic FLOPs counted once although 3 bf16 passes are issued",
-            "ms_per_launch": gms,
-            "step_tensor_frac": F / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
+    lstm_ms, lstm_flop = time_lstm_kernels()
+    peak = peaks["bf16_tflops"]
+    roof = {"bound": "tensor", "kernel": "k_lstm_v2<backward> persistent tcgen05 LSTM recurrence (dominant kernel: 4 LSTM launches = "
+            "%.0f%% of the step; B=32 nh=1024, 200 dependent time steps per launch)" % (100.0 * 2 * (lstm_ms["fwd"] + lstm_ms["bwd"]) / ms_per_step),
+            "achieved": lstm_flop / (lstm_ms["bwd"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": lstm_flop / (lstm_ms["bwd"] * 1e-3) / 1e12 / peak, "traffic": None,
+            "peak_source": peak_src + " bf16 burst (kernel timed alone with CUDA events on the launching stream)",
+            "ms_per_launch": lstm_ms["bwd"], "us_per_time_step": 1e3 * lstm_ms["bwd"] / (c["T"] + 1),
+            "note": "sequential-dependency latency bound, not a throughput kernel: each of the 200 steps is all-gather -> "
+                    "64 tcgen05.mma -> cluster DSMEM reduce -> cell -> grid barrier (profiles/README.md); algorithmic FLOPs "
+                    "2*B*nh*4nh*T counted once (3 split-bf16 passes issued)",
+            "forward": {"ms_per_launch": lstm_ms["fwd"], "achieved": lstm_flop / (lstm_ms["fwd"] * 1e-3) / 1e12},
+            "gemm": {"kernel": "k_gemm_tc<K-major,K-major> vocab projection 6368x20001x1024 (split-bf16, 3 MMA passes)",
+                     "bound": "tensor", "achieved": gflop / (gms * 1e-3) / 1e12, "peak": peak,
+                     "frac": gflop / (gms * 1e-3) / 1e12 / peak, "ms_per_launch": gms,
+                     "mma_rate_frac": 3 * gflop / (gms * 1e-3) / 1e12 / peak},
+            "step_tensor_frac": F / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peak)}
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split operands, f32 accumulate/state", "data": "synthetic",
