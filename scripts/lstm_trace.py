@@ -27,12 +27,15 @@ def summarize(name, steps):
     t0 = d[:, 0]
     per_step = (t0[1:] - t0[:-1])
     sel = slice(5, steps - 1)
-    names = ["first stage landed", "all MMAs issued", "accumulators complete", "epilogue stores issued", "next step start"]
-    cols = [d[:, 1] - d[:, 0], d[:, 2] - d[:, 0], d[:, 3] - d[:, 0], d[:, 4] - d[:, 0]]
+    names = ["first stage landed", "all MMAs issued", "accumulators complete", "partials in shared memory",
+             "cluster barrier passed", "cell done, stores issued", "proxy fence done"]
+    cols = [d[:, i] - d[:, 0] for i in (1, 2, 3, 5, 6, 7, 4)]
     out.append("%s: Bd=%d nh=%d  mean step = %.0f cycles" % (name, Bd, nh, float(per_step[sel].mean())))
-    for n, c in zip(names[:4], cols):
+    for n, c in zip(names, cols):
+        if float(d[sel, 5].abs().max()) == 0.0 and n in names[3:6]:
+            continue                      # v1 kernels do not record the cluster phases
         out.append("   %-28s +%7.0f cycles (mean offset from step start)" % (n, float(c[sel].mean())))
-    out.append("   %-28s +%7.0f cycles" % (names[4], float(per_step[sel].mean())))
+    out.append("   %-28s +%7.0f cycles" % ("next step start", float(per_step[sel].mean())))
 
 
 for rep in range(2):

@@ -60,7 +60,9 @@ def test_split_bf16():
 
 
 TC_SHAPES = [(128, 128, 64), (256, 384, 192), (200, 130, 100), (129, 257, 72), (1000, 96, 520), (64, 520, 4096),
-             (4096, 64, 160)]
+             (4096, 64, 160),
+             # >= 2 x 148 tiles of 128x256: the wide-tile (BN=256, 2-stage) variant; ragged M, N and K
+             (2048, 4864, 128), (2500, 4000, 200), (6368, 1536 + 40, 72)]
 
 
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)

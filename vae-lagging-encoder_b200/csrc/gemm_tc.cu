@@ -17,6 +17,7 @@
 #include "lagvae_common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace lagvae {
@@ -65,15 +66,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;            // 16 KiB per operand part
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi A_lo B_hi B_lo
+constexpr int BM = 128, BK = 64, UK = 16;
+constexpr int TILE_BYTES = BM * BK * 2;            // 16 KiB: one 128-row operand part
+// Two tile shapes: 128x128 (3-stage ring of 64 KiB) and 128x256 (2-stage ring of 96 KiB).  The split-bf16 operands
+// (hi + lo) make these GEMMs L2->SM bandwidth bound (profiles/README.md): the wide tile moves 25% fewer operand bytes
+// per MMA and is used whenever the problem still yields >= 2 waves of tiles.
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 2;
+  static constexpr int B_PART = BN * BK * 2;                         // one B operand part
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_PART;    // A_hi A_lo B_hi B_lo
+  static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
+};
 constexpr int CSTRIDE = 36;                        // floats per staged row (32 + 4 pad: conflict-free float4 both ways)
 constexpr int CSTAGE_BYTES = 4 * 32 * CSTRIDE * 4; // epilogue staging: 4 warps x 32 rows
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CSTAGE_BYTES;
+template <int BN>
+constexpr int smem_bytes() { return TileCfg<BN>::STAGES * TileCfg<BN>::STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CSTAGE_BYTES; }
 constexpr int NTHREADS = 192;
-constexpr int TMEM_COLS = 256;
 
 struct GemmArgs {
   float* C;
@@ -87,11 +96,13 @@ struct GemmArgs {
   const int32_t* row_map;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
           const GemmArgs g) {
+  constexpr int STAGES = TileCfg<BN>::STAGES, STAGE_BYTES = TileCfg<BN>::STAGE_BYTES, B_PART = TileCfg<BN>::B_PART;
+  constexpr int TMEM_COLS = TileCfg<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -138,14 +149,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (three ? 4u : 2u) * TILE_BYTES;
+      const uint32_t tx_bytes = (three ? 2u : 1u) * (uint32_t)(TILE_BYTES + B_PART);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mb = tile % m_blks, nb = tile / m_blks;
         const int m0 = mb * BM, n0 = nb * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
-          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sb_hi + B_PART;
           const int k0 = kb * BK;
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(full_bar(stage), tx_bytes);
@@ -163,12 +174,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             if (!B_MN) {
               ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), k0, n0);
               if (three) ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), k0, n0);
-            } else {
-              ptx::tma_load_2d(sb_hi, &tm_b_hi, full_bar(stage), n0, k0);
-              ptx::tma_load_2d(sb_hi + TILE_BYTES / 2, &tm_b_hi, full_bar(stage), n0 + 64, k0);
-              if (three) {
-                ptx::tma_load_2d(sb_lo, &tm_b_lo, full_bar(stage), n0, k0);
-                ptx::tma_load_2d(sb_lo + TILE_BYTES / 2, &tm_b_lo, full_bar(stage), n0 + 64, k0);
+            } else {   // stored [K, N]: BN/64 boxes of 64(N) x 64(K)
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) {
+                ptx::tma_load_2d(sb_hi + j * 8192, &tm_b_hi, full_bar(stage), n0 + 64 * j, k0);
+                if (three) ptx::tma_load_2d(sb_lo + j * 8192, &tm_b_lo, full_bar(stage), n0 + 64 * j, k0);
               }
             }
           }
@@ -198,7 +208,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t sa_hi = smem_base + stage * STAGE_BYTES, sa_lo = sa_hi + TILE_BYTES;
-          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sa_hi + 3 * TILE_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * TILE_BYTES, sb_lo = sb_hi + B_PART;
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
@@ -308,15 +318,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 int launch(const CUtensorMap* tm, const GemmArgs& g, int grid, cudaStream_t st) {
-  auto kern = k_gemm_tc<A_MN, B_MN>;
+  auto kern = k_gemm_tc<A_MN, B_MN, BN>;
   static bool configured = false;
   if (!configured) {
-    LV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    LV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
     configured = true;
   }
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], g);
+  kern<<<grid, NTHREADS, smem_bytes<BN>(), st>>>(tm[0], tm[1], tm[2], tm[3], g);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }
@@ -342,8 +352,12 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M
   LV_CHECK_ARG(passes == 1 || passes == 3, "gemm_tc: passes must be 1 or 3");
   LV_CHECK_ARG(A.hi && B.hi && (passes == 1 || (A.lo && B.lo)), "gemm_tc: missing operand part");
   LV_CHECK_ARG(bias_rows == nullptr || bias_period > 0, "gemm_tc: bias_period");
+  // tile shape: the wide 128x256 tile when it still gives every SM at least two tiles
+  static const int force_bn = [] { const char* e = getenv("LAGVAE_GEMM_BN"); return e ? atoi(e) : 0; }();
+  const int64_t tiles256 = cdiv(M, BM) * cdiv(N, 256);
+  const int BN = force_bn ? force_bn : ((N >= 256 && tiles256 >= 2 * num_sms()) ? 256 : 128);
   CUtensorMap tm[4];
-  // K-major operand: tensor [rows=MN, cols=K], box 64(K) x 128(rows).
+  // K-major operand: tensor [rows=MN, cols=K], box 64(K) x rows(128 | BN).
   // MN-major operand: tensor [rows=K, cols=MN], box 64(MN) x 64(K rows).
   const void* parts[4] = {A.hi, passes == 3 ? A.lo : A.hi, B.hi, passes == 3 ? B.lo : B.hi};
   for (int i = 0; i < 4; ++i) {
@@ -358,10 +372,21 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M
   GemmArgs g{C, ldc, M, N, K, passes, alpha, beta, bias_n, bias_rows, bias_period, out_row_map};
   const int tiles = (int)(cdiv(M, BM) * cdiv(N, BN));
   const int grid = std::min(tiles, num_sms());
-  if (!A.mn_major && !B.mn_major) return launch<false, false>(tm, g, grid, st);
-  if (!A.mn_major && B.mn_major) return launch<false, true>(tm, g, grid, st);
-  if (A.mn_major && !B.mn_major) return launch<true, false>(tm, g, grid, st);
-  return launch<true, true>(tm, g, grid, st);
+  const int key = (A.mn_major ? 2 : 0) | (B.mn_major ? 1 : 0);
+  if (BN == 256) {
+    switch (key) {
+      case 0: return launch<false, false, 256>(tm, g, grid, st);
+      case 1: return launch<false, true, 256>(tm, g, grid, st);
+      case 2: return launch<true, false, 256>(tm, g, grid, st);
+      default: return launch<true, true, 256>(tm, g, grid, st);
+    }
+  }
+  switch (key) {
+    case 0: return launch<false, false, 128>(tm, g, grid, st);
+    case 1: return launch<false, true, 128>(tm, g, grid, st);
+    case 2: return launch<true, false, 128>(tm, g, grid, st);
+    default: return launch<true, true, 128>(tm, g, grid, st);
+  }
 }
 
 }  // namespace lagvae

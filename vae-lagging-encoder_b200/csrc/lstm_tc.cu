@@ -777,7 +777,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
     }
     if (has_rec) {
       acc_par ^= 1;
+      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 5] = clock64();       // own partials in shared memory
       cluster_sync_all();     // every CTA of the cluster has published its partials (release/acquire, all threads)
+      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 6] = clock64();       // cluster barrier passed
     }
 
     if (warp < 4) {
@@ -876,6 +878,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
           }
         }
       }
+      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();       // cell done, stores issued
       ptx::fence_proxy_async_all();   // the operand of the next step is read by TMA (async proxy) on other SMs
       if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
     }
