@@ -7,4 +7,4 @@ TAILN=25 run k_lstm 240 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k 
 if [ $? -ne 0 ]; then export LAGVAE_NO_LSTM_TC=1; echo "!!! tensor-core unit tests failed -> LAGVAE_NO_LSTM_TC=1"; fi
 TAILN=25 run p_tc 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not simt" --timeout 400
 TAILN=20 run trace 300 python scripts/lstm_trace.py
-run bench 900 python bench.py --steps 10 --warmup 3
+run bench 900 python bench.py --steps 10 --warmup 3 ${BENCH_FLAGS:---no-cpu}

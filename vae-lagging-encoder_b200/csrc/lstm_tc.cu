@@ -528,6 +528,31 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank
   return v;
 }
 
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float x, float y, float z, float w) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// Receive-slot protocol: a slot word holds RX_EMPTY (a NaN payload no arithmetic produces) until the contributor's
+// 16-byte DSMEM store lands; the owner polls the data itself and re-arms the slot after reading it.  No fence, barrier
+// or mbarrier round trip sits between the contributor's tcgen05.ld and the owner's cell update.
+constexpr uint32_t RX_EMPTY = 0xFFFFA5C3u;
+__device__ __forceinline__ float4 ld_shared_volatile_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t x) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(x) : "memory");
+}
+__device__ __forceinline__ bool rx_ready(const float4& v) {
+  return __float_as_uint(v.x) != RX_EMPTY && __float_as_uint(v.y) != RX_EMPTY && __float_as_uint(v.z) != RX_EMPTY &&
+         __float_as_uint(v.w) != RX_EMPTY;
+}
+
 template <bool FWD, int CS_>
 struct V2Cfg {
   static constexpr int CS = CS_;                  // cluster size = K split (forward 4; backward 8, or 4 when 16 clusters of 8 do not fit)
@@ -535,7 +560,7 @@ struct V2Cfg {
   static constexpr int NC = CS * NOWN;            // columns of the cluster (128 | 64)
   static constexpr int NALL = 2 * NC;             // merged hi+lo weight rows = MMA N (256 | 128)
   static constexpr int WT = NALL * 128;           // bytes of one weight tile (one 64-wide k-block)
-  static constexpr int PSTRIDE = NC + 4;          // floats per row of the partial buffer
+  static constexpr int RROW = NOWN + 4;           // floats per row of a receive slot (owned columns + bank padding)
 };
 
 template <bool FWD, int CS_>
@@ -552,14 +577,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
   Smem sm;
   sm.a_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   sm.w_base = sm.a_base + (uint32_t)a.NS * 2 * a.part_bytes;
-  const uint32_t p_base = sm.w_base + (uint32_t)KBS * C::WT;                       // partial buffer [m_tiles*rows][PSTRIDE] fp32
-  sm.bar_base = p_base + (uint32_t)(a.m_tiles * rows_alloc * C::PSTRIDE * 4);
-  uint8_t* gen_w = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
-  float* P = (float*)(smem_raw + (p_base - ptx::smem_u32(smem_raw)));
+  // "receive slots": every CTA of the cluster PUSHES the partial sums of the columns another CTA owns straight into that
+  // CTA's shared memory (st.shared::cluster) and arrives on its mbarrier; the owner then reduces locally.
+  const int rows_tot = a.m_tiles * rows_alloc;
+  const uint32_t r_base = sm.w_base + (uint32_t)KBS * C::WT;                       // [nslots][rows_tot][RROW] fp32
   // "stacked M" (Bd <= 32): the ring stage is [hi rows ; lo rows] contiguously, so ONE M=64 MMA whose A descriptor
   // starts at the hi part covers both operand parts: D rows [0,ra) = A_hi·[W_hi;W_lo], rows [ra,2ra) = A_lo·[W_hi;W_lo];
   // the epilogue adds D[b,0:NC] + D[b,NC:2NC] + D[ra+b,0:NC].  Halves the tcgen05.mma count per time step.
   const bool stack = a.m_tiles == 1 && 2 * rows_alloc <= 64;
+  const int nslots = C::CS * (stack ? 2 : 1);                                      // contributors per owned value
+  sm.bar_base = r_base + (uint32_t)(nslots * rows_tot * C::RROW * 4);
+  uint8_t* gen_w = smem_raw + (sm.w_base - ptx::smem_u32(smem_raw));
   const int tmem_need = a.m_tiles * C::NALL;
   const int tmem_cols = tmem_need <= 128 ? 128 : (tmem_need <= 256 ? 256 : 512);
 
@@ -586,6 +614,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
       store_bf16x8((__nv_bfloat16*)(tile + sw128(j, c)), (__nv_bfloat16*)(tile + sw128(C::NC + j, c)), v);
     }
   }
+  for (int i = threadIdx.x; i < nslots * rows_tot * C::RROW / 4; i += NTHREADS) st_shared_u4(r_base + 16u * i, RX_EMPTY);
   common_prologue(a, sm, tmem_cols, nullptr);
   const uint32_t tmem_base = *(uint32_t*)(gen_w + (sm.tmem_slot(a.NS) - sm.w_base));
   const int64_t slot_elems = (int64_t)2 * Bd * a.KP;
@@ -601,16 +630,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
     for (int i = threadIdx.x; i < Bd * 8; i += NTHREADS) a.dc[(int64_t)(i >> 3) * nh + u0 + (i & 7)] = 0.f;
   }
   ptx::fence_proxy_async_all();
-  unsigned epoch = 0;
-  cluster_sync_all();                                // peers' smem (partial buffers, barriers) exist before any DSMEM access
-  grid_barrier(a.bar, (++epoch) * gridDim.x);
+  cluster_sync_all();                                // peers' smem (receive slots, barriers) exist before any DSMEM access
+  grid_barrier(a.bar, gridDim.x);                    // epoch 1: initial operand published; step s ends epoch s + 2
 
   PipeState ps{0, 0};
   const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   const int nsteps = FWD ? Tn : Tn + (a.want_init ? 1 : 0);
   int acc_par = 0;
+  // Per-step synchronisation (no CTA-wide barrier inside the loop): the epilogue warps arrive on the grid counter as
+  // soon as the next operand is stored; only the TMA producer warp polls it.  The MMA warp is gated by the ring's
+  // mbarriers, the epilogue warps by the accumulator mbarrier, and every re-use (TMEM accumulator, receive slots,
+  // operand double buffer) is ordered behind the arrival of ALL CTAs for the previous step.
   for (int s = 0; s < nsteps; ++s) {
-    if (trace && threadIdx.x == 0) a.dbg[s * 8 + 0] = clock64();
     const int t = FWD ? s : Tn - 1 - s;              // backward: t = -1 on the extra step that only produces d h_{-1}
     const bool has_rec = FWD ? true : s > 0;
     const int rd_slot = (s + 1) & 1;
@@ -659,6 +690,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
 
     if (warp == 5) {
       // ------------------------------- TMA producer: this CTA's K slice of the streamed operand
+      if (s > 0) {                       // every CTA has stored its part of this step's operand
+        if (lane == 0) {
+          const unsigned target = (unsigned)(s + 1) * gridDim.x;
+          while (ld_acquire_u32(a.bar) < target) {
+          }
+        }
+        __syncwarp();
+      }
+      if (trace && lane == 0) a.dbg[s * 8 + 0] = clock64();   // step start = grid counter complete
       if (has_rec) {
         ptx::fence_proxy_async_all();
         for (int mt = 0; mt < a.m_tiles; ++mt)
@@ -704,126 +744,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
         }
         if (trace && lane == 0) a.dbg[s * 8 + 2] = clock64();
       }
-    } else if (has_rec) {
-      // ------------------------------- epilogue part 1: partial products TMEM -> registers -> shared memory
-      for (int mt = 0; mt < a.m_tiles; ++mt) {
-        ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)acc_par);
-        ptx::tc_fence_after();
-        if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
-        const int rloc = warp * 16 + (lane & 15);          // MMA row inside the m-tile (TMEM lane 32*warp + lane%16)
-        if (!stack) {
-          float* prow = P + (size_t)(mt * rows_alloc + rloc) * C::PSTRIDE;
-          const bool wr_ok = lane < 16 && rloc < rows_alloc;
-#pragma unroll 1
-          for (int cb = 0; cb < C::NC; cb += 32) {
-            uint32_t r1[32], r2[32];
-            ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + cb), r1);
-            ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL + C::NC + cb), r2);
-            ptx::tmem_ld_wait();
-            if (wr_ok) {
+    } else {
+      // =============================== epilogue warps 0-3 ===============================
+      if (has_rec) {
+        // ---- part 1: partial products TMEM -> registers -> PUSH to the owner's receive slot (DSMEM store)
+        const int nrow_mma = stack ? 2 * rows_alloc : rows_alloc;          // MMA rows of an m-tile that carry data
+        for (int mt = 0; mt < a.m_tiles; ++mt) {
+          ptx::mbar_wait(sm.acc(mt, a.NS), (uint32_t)acc_par);
+          ptx::tc_fence_after();
+          if (trace && threadIdx.x == 0 && mt == 0) a.dbg[s * 8 + 3] = clock64();
+          if (warp * 16 < nrow_mma) {                                      // warp-uniform
+            const int rloc = warp * 16 + (lane & 15);                      // MMA row (TMEM lane 32*warp + lane%16)
+            const bool lo_row = stack && rloc >= rows_alloc;               // stacked M: rows [ra, 2ra) = A_lo · [W_hi ; W_lo]
+            const bool valid = lane < 16 && rloc < nrow_mma;
+            const int brow = mt * rows_alloc + (lo_row ? rloc - rows_alloc : rloc);
+            const int slot = stack ? 2 * (int)rank + (lo_row ? 1 : 0) : (int)rank;
+            const uint32_t dst_local = r_base + (uint32_t)(((slot * rows_tot + brow) * C::RROW) * 4);
+            const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * C::NALL);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
-                                                         __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
-                                                         __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
-                                                         __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
-            }
-          }
-        } else {
-          // phase 1: hi rows (MMA row r < ra = batch row r): P[r] = D[r,0:NC] + D[r,NC:2NC]
-          const bool hi_row = lane < 16 && rloc < rows_alloc;
-          const bool lo_row = lane < 16 && rloc >= rows_alloc && rloc < 2 * rows_alloc;
-          float* prow = P + (size_t)(hi_row ? rloc : (lo_row ? rloc - rows_alloc : 0)) * C::PSTRIDE;
-          const bool any_hi = warp * 16 < rows_alloc, any_lo = warp * 16 + 15 >= rows_alloc && warp * 16 < 2 * rows_alloc;
-          if (any_hi) {
-#pragma unroll 1
-            for (int cb = 0; cb < C::NC; cb += 32) {
-              uint32_t r1[32], r2[32];
-              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r1);
-              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::NC + cb), r2);
-              ptx::tmem_ld_wait();
-              if (hi_row) {
+            for (int qq = 0; qq < C::CS; ++qq) {
+              const uint32_t q = (rank + 1u + (uint32_t)qq) % (uint32_t)C::CS;   // peers first, own columns last
+              const uint32_t dst = mapa_u32(dst_local, q);
+              if (FWD) {
+                uint32_t r1[32], r2[32];
+                ptx::tmem_ld32(tbase + q * 32u, r1);
+                ptx::tmem_ld32(tbase + (uint32_t)C::NC + q * 32u, r2);
+                ptx::tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *(float4*)(prow + cb + j) = make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]),
-                                                           __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
-                                                           __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
-                                                           __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
-              }
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps: phase-1 rows are in P
-          // phase 2: lo rows (MMA row ra + b): P[b] += D[ra+b, 0:NC]
-          if (any_lo) {
-#pragma unroll 1
-            for (int cb = 0; cb < C::NC; cb += 32) {
-              uint32_t r1[32];
-              ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r1);
-              ptx::tmem_ld_wait();
-              if (lo_row) {
+                  for (int j = 0; j < 32; j += 4) {
+                    float v[4];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 v = *(float4*)(prow + cb + j);
-                  v.x += __uint_as_float(r1[j]); v.y += __uint_as_float(r1[j + 1]);
-                  v.z += __uint_as_float(r1[j + 2]); v.w += __uint_as_float(r1[j + 3]);
-                  *(float4*)(prow + cb + j) = v;
+                    for (int e = 0; e < 4; ++e)
+                      v[e] = __uint_as_float(r1[j + e]) + (lo_row ? 0.f : __uint_as_float(r2[j + e]));   // lo·lo dropped
+                    st_cluster_f4(dst + (uint32_t)j * 4u, v[0], v[1], v[2], v[3]);
+                  }
+                }
+              } else {
+                uint32_t r1[8], r2[8];
+                tmem_ld8(tbase + q * 8u, r1);
+                tmem_ld8(tbase + (uint32_t)C::NC + q * 8u, r2);
+                ptx::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 8; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                      v[e] = __uint_as_float(r1[j + e]) + (lo_row ? 0.f : __uint_as_float(r2[j + e]));
+                    st_cluster_f4(dst + (uint32_t)j * 4u, v[0], v[1], v[2], v[3]);
+                  }
                 }
               }
             }
           }
         }
+        ptx::tc_fence_before();
+        acc_par ^= 1;
+        if (trace && threadIdx.x == 0) a.dbg[s * 8 + 5] = clock64();       // own partials pushed
       }
-      ptx::tc_fence_before();
-    }
-    if (has_rec) {
-      acc_par ^= 1;
-      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 5] = clock64();       // own partials in shared memory
-      cluster_sync_all();     // every CTA of the cluster has published its partials (release/acquire, all threads)
-      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 6] = clock64();       // cluster barrier passed
-    }
 
-    if (warp < 4) {
-      // ------------------------------- epilogue part 2: DSMEM reduce of the owned columns + LSTM cell, 4 units/thread
-      for (int it = threadIdx.x; it < items; it += 128) {     // item = (batch row, unit quad)
-        if (it != (int)threadIdx.x) load_inputs(it);
-        const int b = it >> 1, uq = it & 1, ub = u0 + uq * 4;
-        const int mt = b >> 6, rloc = b & 63;
-        const uint32_t prow = p_base + (uint32_t)((mt * rows_alloc + rloc) * C::PSTRIDE * 4);
-        if (FWD) {
-          // issue every distributed-shared-memory load before consuming any (each is ~200+ cycles of latency)
-          float4 pv[C::CS * 4];
-#pragma unroll
-          for (int rr = 0; rr < C::CS; ++rr)
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              pv[rr * 4 + g] = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 32 + g * 8 + uq * 4) * 4), (uint32_t)rr);
-          float my[16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float4 acc4 = pv[g];
-#pragma unroll
-            for (int rr = 1; rr < C::CS; ++rr) {
-              acc4.x += pv[rr * 4 + g].x; acc4.y += pv[rr * 4 + g].y; acc4.z += pv[rr * 4 + g].z; acc4.w += pv[rr * 4 + g].w;
-            }
-            my[g * 4 + 0] = acc4.x; my[g * 4 + 1] = acc4.y; my[g * 4 + 2] = acc4.z; my[g * 4 + 3] = acc4.w;
-          }
+      // ---- part 2: local reduce of the receive slots + LSTM cell, 4 units per thread.  Only the bf16 operand of the
+      // next time step is stored before the grid-barrier arrival; everything else (fp32 stashes for the later
+      // kernels) is stored after it, off the inter-SM critical path (single-item threads only).
+      const bool defer = items <= 128;
+      const uint32_t slot_bytes = (uint32_t)(rows_tot * C::RROW * 4);
+      if (FWD) {
+        float hv[4], cv[4], act[16];
+        auto store_rest = [&](int it) {
+          const int b = it >> 1, ub = u0 + (it & 1) * 4;
           float* g = a.gates + ((int64_t)t * Bd + b) * 4 * nh + ub;
-          const float (&pre)[16] = pin;
-          const float (&cp)[4] = pc;
-          float hv[4], cv[4], act[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ig = fsigmoid(pre[j] + my[j]);
-            const float fg = fsigmoid(pre[4 + j] + my[4 + j]);
-            const float gg = ftanh(pre[8 + j] + my[8 + j]);
-            const float og = fsigmoid(pre[12 + j] + my[12 + j]);
-            const float c = fg * cp[j] + ig * gg;
-            cv[j] = c;
-            hv[j] = og * ftanh(c);
-            act[j] = ig; act[4 + j] = fg; act[8 + j] = gg; act[12 + j] = og;
-          }
-          __nv_bfloat16* d = wr + (int64_t)b * a.KP + ub;
-          store_bf16x4(d, d + (int64_t)Bd * a.KP, hv);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             *(float4*)(g + q * nh) = make_float4(act[q * 4], act[q * 4 + 1], act[q * 4 + 2], act[q * 4 + 3]);
@@ -836,27 +826,117 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
             for (int j = 0; j < 4; ++j) hd[j] = hv[j] * drop_factor(a.drop, ((uint64_t)b * Tn + t) * nh + ub + j);
             *(float4*)(a.hdrop_all + o) = make_float4(hd[0], hd[1], hd[2], hd[3]);
           }
-        } else {
-          float rec[4] = {0.f, 0.f, 0.f, 0.f};
-          if (has_rec) {
-            float4 pv[C::CS];
+        };
+        for (int it = threadIdx.x; it < items; it += 128) {     // item = (batch row, unit quad)
+          if (it != (int)threadIdx.x) load_inputs(it);
+          const int b = it >> 1, uq = it & 1, ub = u0 + uq * 4;
+          const uint32_t rrow = r_base + (uint32_t)((((b >> 6) * rows_alloc + (b & 63)) * C::RROW + uq * 4) * 4);
+          float my[16];
+          {
+            float4 pv[2 * C::CS][4];
+            bool ok;
+            unsigned spins = 0;
+            do {                                  // all loads in flight, then test; retry until every contributor landed
+              if (++spins > (1u << 26)) asm volatile("trap;");   // a lost contribution must not hang the device
+              ok = true;
 #pragma unroll
-            for (int rr = 0; rr < C::CS; ++rr)
-              pv[rr] = ld_dsmem_f4(prow + (uint32_t)(((int)rank * 8 + uq * 4) * 4), (uint32_t)rr);
+              for (int sl = 0; sl < 2 * C::CS; ++sl)
+                if (sl < nslots) {
 #pragma unroll
-            for (int rr = 0; rr < C::CS; ++rr) { rec[0] += pv[rr].x; rec[1] += pv[rr].y; rec[2] += pv[rr].z; rec[3] += pv[rr].w; }
+                  for (int g = 0; g < 4; ++g) pv[sl][g] = ld_shared_volatile_f4(rrow + (uint32_t)sl * slot_bytes + g * 32u);
+                }
+#pragma unroll
+              for (int sl = 0; sl < 2 * C::CS; ++sl)
+                if (sl < nslots) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) ok = ok && rx_ready(pv[sl][g]);
+                }
+            } while (!ok);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float4 acc4 = pv[0][g];
+#pragma unroll
+              for (int sl = 1; sl < 2 * C::CS; ++sl)
+                if (sl < nslots) { acc4.x += pv[sl][g].x; acc4.y += pv[sl][g].y; acc4.z += pv[sl][g].z; acc4.w += pv[sl][g].w; }
+              my[g * 4 + 0] = acc4.x; my[g * 4 + 1] = acc4.y; my[g * 4 + 2] = acc4.z; my[g * 4 + 3] = acc4.w;
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2 * C::CS; ++sl)
+              if (sl < nslots) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) st_shared_u4(rrow + (uint32_t)sl * slot_bytes + g * 32u, RX_EMPTY);   // re-arm
+              }
           }
+          if (trace && threadIdx.x == 0) a.dbg[s * 8 + 6] = clock64();     // every contributor's partial has landed
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ig = fsigmoid(pin[j] + my[j]);
+            const float fg = fsigmoid(pin[4 + j] + my[4 + j]);
+            const float gg = ftanh(pin[8 + j] + my[8 + j]);
+            const float og = fsigmoid(pin[12 + j] + my[12 + j]);
+            const float c = fg * pc[j] + ig * gg;
+            cv[j] = c;
+            hv[j] = og * ftanh(c);
+            act[j] = ig; act[4 + j] = fg; act[8 + j] = gg; act[12 + j] = og;
+          }
+          __nv_bfloat16* d = wr + (int64_t)b * a.KP + ub;
+          store_bf16x4(d, d + (int64_t)Bd * a.KP, hv);            // critical: operand of step s+1 on every SM
+          if (!defer) store_rest(it);
+        }
+        if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();       // cell done, operand stores issued
+        ptx::fence_proxy_async_all();   // the operand of the next step is read by TMA (async proxy) on other SMs
+        if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
+        asm volatile("bar.sync 1, 128;" ::: "memory");                     // the 4 epilogue warps
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+        // the release's membar drains the SM's write queue: keep the non-critical stores behind it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (defer && (int)threadIdx.x < items) store_rest((int)threadIdx.x);
+      } else {
+        float dg[16], dcn[4], rec[4];
+        auto store_rest = [&](int it) {
+          const int b = it >> 1, ub = u0 + (it & 1) * 4;
           if (t < 0) {
             *(float4*)(a.dh_rec_out + (int64_t)b * nh + ub) = make_float4(rec[0], rec[1], rec[2], rec[3]);
           } else {
-            const float (&gt)[16] = pin;
-            const int64_t o = ((int64_t)t * Bd + b) * nh + ub;
-            (void)o;
-            float dg[16], dcn[4];
+            float* go = a.dgates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *(float4*)(go + q * nh) = make_float4(dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]);
+            *(float4*)(a.dc + (int64_t)b * nh + ub) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+          }
+        };
+        for (int it = threadIdx.x; it < items; it += 128) {
+          if (it != (int)threadIdx.x) load_inputs(it);
+          const int b = it >> 1, uq = it & 1, ub = u0 + uq * 4;
+          rec[0] = rec[1] = rec[2] = rec[3] = 0.f;
+          if (has_rec) {
+            const uint32_t rrow = r_base + (uint32_t)((((b >> 6) * rows_alloc + (b & 63)) * C::RROW + uq * 4) * 4);
+            float4 pv[2 * C::CS];
+            bool ok;
+            unsigned spins = 0;
+            do {
+              if (++spins > (1u << 26)) asm volatile("trap;");
+              ok = true;
+#pragma unroll
+              for (int sl = 0; sl < 2 * C::CS; ++sl)
+                if (sl < nslots) pv[sl] = ld_shared_volatile_f4(rrow + (uint32_t)sl * slot_bytes);
+#pragma unroll
+              for (int sl = 0; sl < 2 * C::CS; ++sl)
+                if (sl < nslots) ok = ok && rx_ready(pv[sl]);
+            } while (!ok);
+#pragma unroll
+            for (int sl = 0; sl < 2 * C::CS; ++sl)
+              if (sl < nslots) {
+                rec[0] += pv[sl].x; rec[1] += pv[sl].y; rec[2] += pv[sl].z; rec[3] += pv[sl].w;
+                st_shared_u4(rrow + (uint32_t)sl * slot_bytes, RX_EMPTY);   // re-arm
+              }
+            if (trace && threadIdx.x == 0) a.dbg[s * 8 + 6] = clock64();
+          }
+          if (t >= 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float cc = pc[j], cpv = pc2[j], dcv = pdc[j], e = pe[j];
-              const float ig = gt[j], fg = gt[4 + j], gg = gt[8 + j], og = gt[12 + j];
+              const float ig = pin[j], fg = pin[4 + j], gg = pin[8 + j], og = pin[12 + j];
               const float dh = rec[j] + e;
               const float tc = ftanh(cc);
               const float dct = dcv + dh * og * (1.f - tc * tc);
@@ -866,24 +946,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
               dg[12 + j] = dh * tc * og * (1.f - og);
               dcn[j] = dct * fg;
             }
-            float* go = a.dgates + ((int64_t)t * Bd + b) * 4 * nh + ub;
             __nv_bfloat16* wb = wr + (int64_t)b * a.KP + ub;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              *(float4*)(go + q * nh) = make_float4(dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]);
+            for (int q = 0; q < 4; ++q) {       // critical: operand of step s+1 on every SM
               float seg[4] = {dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]};
               store_bf16x4(wb + q * nh, wb + q * nh + (int64_t)Bd * a.KP, seg);
             }
-            *(float4*)(a.dc + (int64_t)b * nh + ub) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
           }
+          if (!defer) store_rest(it);
         }
+        if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();
+        ptx::fence_proxy_async_all();
+        if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+        // the release's membar drains the SM's write queue: keep the non-critical stores behind it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (defer && (int)threadIdx.x < items) store_rest((int)threadIdx.x);
       }
-      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();       // cell done, stores issued
-      ptx::fence_proxy_async_all();   // the operand of the next step is read by TMA (async proxy) on other SMs
-      if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
     }
-    grid_barrier(a.bar, (++epoch) * gridDim.x);   // also orders peers' DSMEM reads before the next overwrite of P
-    ptx::tc_fence_after();
   }
   cluster_sync_all();                              // no CTA may exit while a peer can still read its shared memory
   if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
@@ -995,7 +1076,8 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
   const int rows_alloc = Bd >= 64 ? 64 : (int)round_up(Bd, 8);
   const int64_t stage = 2 * (int64_t)rows_alloc * 128;
   const int64_t wbytes = (int64_t)KBS * C::WT;
-  const int64_t pbytes = (int64_t)m_tiles * rows_alloc * C::PSTRIDE * 4;
+  const bool stack = m_tiles == 1 && 2 * rows_alloc <= 64;
+  const int64_t pbytes = (int64_t)C::CS * (stack ? 2 : 1) * m_tiles * rows_alloc * C::RROW * 4;   // receive slots
   int64_t n = (SMEM_LIMIT - wbytes - pbytes - MISC_BYTES) / stage;
   n = std::min<int64_t>(n, MAX_NS);
   n = std::min<int64_t>(n, std::max(KBS * m_tiles, 2));
