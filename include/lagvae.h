@@ -151,6 +151,14 @@ int lagvae_text_inner_step(lagvae_text_plan* plan, const lagvae_text_params* par
                            const lagvae_dropout* drop, float max_norm, float lr, float* grad_ws,
                            float* out_loss, float* out_scalars, void* stream);
 
+/* Data-parallel overlap hook (no counterpart in the single-process reference).  The decoder
+ * gradients (the last 7 tensors of vae.parameters(), 70% of the bucket) are final before the encoder LSTM
+ * backward starts.  With the hook enabled lagvae_text_loss_backward records an internal event at that
+ * point and lagvae_text_wait_decoder_grads makes `stream` wait for it, so that the caller can all-reduce
+ * the decoder part of the flat gradient on a side stream while the encoder backward is still running. */
+int lagvae_text_decoder_grads_event(lagvae_text_plan* plan, int enable);
+int lagvae_text_wait_decoder_grads(lagvae_text_plan* plan, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Building blocks (exported for the unit/parity tests; also what the plan calls internally)
  * ------------------------------------------------------------------------------------------- */

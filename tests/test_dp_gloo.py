@@ -20,8 +20,10 @@ def _setup_path():
 class OracleBackend:
     """CPU stand-in for EngineBackend: gradients from the oracle (test-only)."""
 
-    def __init__(self, eps_global, klw, lo):
+    def __init__(self, eps_global, klw, lo, decoder_offset=None):
         self.eps, self.klw, self.lo = eps_global, klw, lo
+        if decoder_offset is not None:          # two-bucket collective ([decoder | encoder]) as EngineBackend exposes it
+            self.decoder_offset = decoder_offset
 
     def forward_backward(self, params, x, g_scale, flat):
         import lagging_oracle as O
@@ -51,7 +53,7 @@ class OracleBackend:
         return norm
 
 
-def _worker(rank, world, port, B, out_q):
+def _worker(rank, world, port, B, out_q, two_buckets=False):
     _setup_path()
     import lagging_oracle as O
     from lagvae.dp import dp_inner_step, shard_bounds
@@ -64,20 +66,22 @@ def _worker(rank, world, port, B, out_q):
     eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
     flat = torch.zeros(sum(q.numel() for q in params))
     lo, hi = shard_bounds(B, rank, world)
-    loss_sum, norm = dp_inner_step(OracleBackend(eps, 0.5, lo), params, x, flat, max_norm=0.05)
+    dec_off = sum(q.numel() for q in params[:6]) if two_buckets else None
+    loss_sum, norm = dp_inner_step(OracleBackend(eps, 0.5, lo, dec_off), params, x, flat, max_norm=0.05)
     out_q.put((rank, loss_sum, norm, [q.clone() for q in params[:6]]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [6, 5, 1])   # even, ragged, and an empty shard on rank 1
-def test_two_rank_gloo_equals_single_process(B):
+@pytest.mark.parametrize("B,two_buckets", [(6, False), (5, False), (1, False), (5, True), (1, True)])
+def test_two_rank_gloo_equals_single_process(B, two_buckets):
+    """even, ragged, and an empty shard on rank 1; single bucket and the [decoder | encoder] split of the overlap path"""
     _setup_path()
     import lagging_oracle as O
-    world, port = 2, 29000 + os.getpid() % 2000 + B
+    world, port = 2, 29000 + os.getpid() % 2000 + B + (10 if two_buckets else 0)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q, two_buckets)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])

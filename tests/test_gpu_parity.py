@@ -253,3 +253,35 @@ def test_yahoo_shape_against_reference_fingerprints(golden, force_simt):
     m2, l2 = eng.encode_stats(params, x)
     mi = float(eng.mi(m2, l2, torch.from_numpy(g["eps_mi"]).cuda()))
     assert abs(mi - float(g["mi"])) <= OUT_TOL * max(1.0, abs(float(g["mi"])))
+
+
+def test_decoder_gradient_event_fires_when_decoder_grads_are_final(golden):
+    """Data-parallel overlap hook (lagvae.h): a side stream that waits on the decoder-gradient event copies the decoder
+    part of the flat bucket while the encoder backward is still running; the copy must equal the final gradients."""
+    g = golden("aligned_train")
+    c = case_inputs(g)
+    eng = _engine(c, False)
+    params = _plist(case_params(g))
+    x, eps = c["x"].cuda(), c["eps"].cuda()
+    gw = eng.grad_workspace()
+    views = eng.split_grads(gw)
+    off = eng.decoder_offset
+    assert off == sum(p.numel() for p in params[:6])
+    eng.enable_decoder_grads_event(c["B"], x.shape[1], 1)
+    side = torch.cuda.Stream()
+    gl = torch.full((c["B"],), 1.0 / c["B"], device="cuda")
+    for _ in range(2):
+        gw.fill_(float("nan"))
+        eng.loss_forward(params, x, eps, c["klw"], _drop(c, g))
+        eng.loss_backward(params, x, gl, None, None, grads_out=views)
+        eng.wait_decoder_grads(c["B"], x.shape[1], 1, side)
+        with torch.cuda.stream(side):
+            early = gw[off:].clone()
+        torch.cuda.synchronize()
+        assert torch.equal(early, gw[off:])
+        assert bool(torch.isfinite(gw).all())
+    for k, gr in zip(O.ALL_KEYS, views):
+        assert_close(gr, g["g." + k], GRAD_TOL, "grad " + k, floor=1e-7)
+    eng.enable_decoder_grads_event(c["B"], x.shape[1], 1, enable=False)
+    with pytest.raises(Exception):
+        eng.wait_decoder_grads(c["B"], x.shape[1], 1, side)

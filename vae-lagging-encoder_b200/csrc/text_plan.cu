@@ -43,6 +43,8 @@ struct lagvae_text_plan {
   char* arena;
   size_t arena_bytes, arena_off;
   LstmTcState* lstm_tc;  // persistent tcgen05 LSTM state (nullptr when unsupported / SIMT)
+  cudaEvent_t dec_ev;    // optional: recorded when the decoder gradients are final (data-parallel overlap hook)
+  bool dec_ev_recorded;
   // state carried from forward to backward
   lagvae_dropout drop;
   float kl_weight;
@@ -431,7 +433,28 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
 void lagvae_text_plan_destroy(lagvae_text_plan* P) {
   if (!P) return;
   lstm_tc_destroy(P->lstm_tc);
+  if (P->dec_ev) cudaEventDestroy(P->dec_ev);
   delete P;
+}
+
+int lagvae_text_decoder_grads_event(lagvae_text_plan* P, int enable) {
+  LV_CHECK_ARG(P, "decoder_grads_event: null plan");
+  if (enable && !P->dec_ev) {
+    LV_CUDA(cudaEventCreateWithFlags(&P->dec_ev, cudaEventDisableTiming));
+    P->dec_ev_recorded = false;
+  } else if (!enable && P->dec_ev) {
+    LV_CUDA(cudaEventDestroy(P->dec_ev));
+    P->dec_ev = nullptr;
+    P->dec_ev_recorded = false;
+  }
+  return LAGVAE_OK;
+}
+
+int lagvae_text_wait_decoder_grads(lagvae_text_plan* P, void* stream) {
+  LV_CHECK_ARG(P, "wait_decoder_grads: null plan");
+  LV_CHECK_ARG(P->dec_ev && P->dec_ev_recorded, "wait_decoder_grads: hook not enabled or no backward recorded yet");
+  LV_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, P->dec_ev, 0));
+  return LAGVAE_OK;
 }
 
 int lagvae_text_encode_stats(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
@@ -579,6 +602,12 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   LV_TRY(gemm_f32(P->dzb, 4 * nh, 1, w->p[D_WIH] + ni, 1, ni + nz, P->dz, nz, Bd, nz, 4 * nh, 1.f, 0.f, nullptr,
                   nullptr, 0, st));
   LV_TRY(gemm_f32(P->dc0t, nh, 1, w->p[D_TRANS], 1, nz, P->dz, nz, Bd, nz, nh, 1.f, 1.f, nullptr, nullptr, 0, st));
+
+  // all 7 decoder gradients are final here: data-parallel callers may start reducing them (lagvae.h)
+  if (P->dec_ev) {
+    LV_CUDA(cudaEventRecord(P->dec_ev, st));
+    P->dec_ev_recorded = true;
+  }
 
   // ---- reparameterisation + KL + head backward
   LV_TRY(reparam_kl_bwd(P->dz, P->eps, P->mu, P->logvar, P->g_kl, B, nz, ns, P->dml, st));

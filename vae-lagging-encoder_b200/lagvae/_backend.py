@@ -57,6 +57,8 @@ PROTOTYPES = {
     "lagvae_text_param_count": (_i64, [C.POINTER(TextDims)]),
     "lagvae_text_inner_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f,
                                     _vp, _vp, _vp, _vp]),
+    "lagvae_text_decoder_grads_event": (_i, [_vp, _i]),
+    "lagvae_text_wait_decoder_grads": (_i, [_vp, _vp]),
     "lagvae_lstm_workspace_bytes": (_sz, [_i, _i]),
     "lagvae_lstm_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _sz, _vp]),
     "lagvae_lstm_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _vp, _i,

@@ -51,7 +51,24 @@ def dp_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x_globa
         flat_grads.zero_()
         loss_sum = torch.zeros(1, dtype=torch.float32, device=flat_grads.device)
     if world > 1:
-        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)          # the ONE data-path collective
+        # the data-path collective: one sum of the flat gradient.  Back-ends that expose `decoder_offset` get it as two
+        # buckets — [decoder | encoder] — and, when they also provide `decoder_grads_stream()`, the decoder bucket
+        # (70% of the bytes, final before the encoder LSTM backward starts) is reduced on a side stream underneath
+        # the still-running encoder backward.
+        off = getattr(backend, "decoder_offset", None)
+        if off is None:
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+        else:                                   # the bucket split depends on the back-end only: identical on every rank
+            side = (backend.decoder_grads_stream(x_local)
+                    if x_local.shape[0] > 0 and hasattr(backend, "decoder_grads_stream") else None)
+            if side is not None:
+                with torch.cuda.stream(side):
+                    dist.all_reduce(flat_grads[off:], op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(flat_grads[:off], op=dist.ReduceOp.SUM, group=group)
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                dist.all_reduce(flat_grads[off:], op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(flat_grads[:off], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)            # 4 bytes: Σloss for text.py:381
     norm = backend.clip_sgd(params, flat_grads, max_norm, lr)
     return float(loss_sum), norm
@@ -60,15 +77,32 @@ def dp_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x_globa
 class EngineBackend:
     """Product back-end: lagvae.TextEngine kernels; flat_grads is the engine's flat gradient workspace."""
 
-    def __init__(self, engine, kl_weight, eps_fn, drop_fn):
+    def __init__(self, engine, kl_weight, eps_fn, drop_fn, overlap=True):
         self.engine, self.kl_weight, self.eps_fn, self.drop_fn = engine, kl_weight, eps_fn, drop_fn
         self._views = None
+        self.decoder_offset = engine.decoder_offset
+        self._overlap = overlap
+        self._side = None
+        self._hooked = set()
+
+    def decoder_grads_stream(self, x_local):
+        """Side stream that already waits for the decoder gradients of the backward just enqueued (None = no overlap)."""
+        if not self._overlap:
+            return None
+        B, T = int(x_local.shape[0]), int(x_local.shape[1])
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=x_local.device)
+        self.engine.wait_decoder_grads(B, T, 1, self._side)
+        return self._side
 
     def forward_backward(self, params, x, g_scale, flat_grads):
         eng = self.engine
         if self._views is None or self._views[0].data_ptr() != flat_grads.data_ptr():
             self._views = eng.split_grads(flat_grads)
         B = x.shape[0]
+        if self._overlap and (B, x.shape[1]) not in self._hooked:
+            eng.enable_decoder_grads_event(B, x.shape[1], 1)
+            self._hooked.add((B, x.shape[1]))
         loss, _, _ = eng.loss_forward(params, x, self.eps_fn(B), self.kl_weight, self.drop_fn())
         gl = torch.full((B,), g_scale, dtype=torch.float32, device=x.device)
         # aggressive loop: decoder weights are not stepped, their gradients only enter the clip norm

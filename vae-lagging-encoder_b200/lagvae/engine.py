@@ -241,6 +241,24 @@ class TextEngine:
                      "lagvae_clip_sgd_step")
         return norm
 
+    @property
+    def decoder_offset(self):
+        """Index of the first decoder gradient in the flat bucket (encoder tensors come first, as in vae.parameters())."""
+        return sum(self.counts[:6])
+
+    def enable_decoder_grads_event(self, B, T, ns=1, enable=True):
+        """Data-parallel overlap hook (lagvae.h): loss_backward of the (B, T, ns) plan records an event once the 7 decoder
+        gradients are final."""
+        with torch.cuda.device(self.device):
+            be.check(be.lib().lagvae_text_decoder_grads_event(self.plan(B, T, ns), 1 if enable else 0),
+                     "lagvae_text_decoder_grads_event")
+
+    def wait_decoder_grads(self, B, T, ns, stream):
+        """Make `stream` (torch.cuda.Stream) wait for the decoder-gradient event of the last loss_backward."""
+        with torch.cuda.device(self.device):
+            be.check(be.lib().lagvae_text_wait_decoder_grads(self.plan(B, T, ns), C.c_void_p(stream.cuda_stream)),
+                     "lagvae_text_wait_decoder_grads")
+
     def grad_workspace(self):
         return torch.empty(sum(self.counts), dtype=torch.float32, device=self.device)
 
