@@ -256,6 +256,30 @@ int lagvae_gemm_auto(const float* A, int64_t a_rs, int64_t a_cs, const float* B,
                      int64_t ldc, int M, int N, int K, float alpha, float beta, const float* bias_n, void* scratch,
                      size_t scratch_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Im2col-free masked convolution on tcgen05 (csrc/conv_tc.cu) — MaskedConv2d inside PixelCNNBlock
+ * (dec_pixelcnn_v2.py:12-30,39-47): 32 -> 32 channels, k x k (odd, <= 7), stride 1, pad k/2, NHWC.
+ * Activations are staged once per layer in the "cat" format: bf16 [B,H,W,64] = [hi(32) | lo(32)] per pixel
+ * (lagvae_split_cat32, or the fused BatchNorm/ELU kernels below); shifted operand tiles are 4-D TMA boxes with
+ * zero fill outside the image.  mask_mode: 0 plain, 1 mask 'A', 2 mask 'B' (all input channels masked).
+ * Only live taps are multiplied in forward/dgrad; wgrad returns ALL k*k taps in the torch layout [32,32,kh,kw]
+ * (autograd of the reference produces gradients for masked taps as well).
+ * ------------------------------------------------------------------------------------------- */
+int lagvae_conv32_supported(int B, int H, int W, int kh, int kw);
+int lagvae_split_cat32(const float* x, int64_t rows, uint16_t* cat, void* stream);
+size_t lagvae_conv32_wbuf_bytes(int kh, int kw);
+/* w: fp32 [32,32,kh,kw] (torch layout) -> bf16 forward + dgrad weight tiles in wbuf (128-B aligned). */
+int lagvae_conv32_prepare_weights(const float* w, int kh, int kw, int mask_mode, void* wbuf, void* stream);
+/* y fp32 [B,H,W,32]; stats_or_null: device double[64] receiving sum(y) | sum(y^2) per channel (zeroed inside) — the
+ * batch statistics of the BatchNorm that follows the convolution, accumulated in the epilogue. */
+int lagvae_conv32_forward(const uint16_t* xcat, const void* wbuf, int B, int H, int W, int kh, int kw, int mask_mode,
+                          float* y, double* stats_or_null, void* stream);
+int lagvae_conv32_dgrad(const uint16_t* dycat, const void* wbuf, int B, int H, int W, int kh, int kw, int mask_mode,
+                        float* dx, void* stream);
+size_t lagvae_conv32_wgrad_scratch_bytes(int kh, int kw);
+int lagvae_conv32_wgrad(const uint16_t* dycat, const uint16_t* xcat, int B, int H, int W, int kh, int kw, float* dw,
+                        void* scratch, void* stream);
+
 /* materialise the Philox dropout keep-mask the kernels would use (tests feed it to the oracle) */
 int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep,
                         void* stream);

@@ -9,6 +9,7 @@ Layout: activations travel between layers as contiguous NHWC fp32 tensors [B, H,
 torch provides the tape, device memory and the (tiny) weight re-layouts only.  No CPU fallback."""
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -98,6 +99,59 @@ class _ConvFn(torch.autograd.Function):
                 _gemm(dy, Cout, 1, wm, 1, K, dcol, K, R, K, Cout)
                 be.check(be.lib().lagvae_col2im(be.ptr(dcol), B, H, W, Cin, kh, kw, stride, pad, be.ptr(dx), _st()), "lagvae_col2im")
         return dx, dw, None, None
+
+
+def _conv32_ok(x, weight, stride, pad):
+    """The tcgen05 im2col-free kernel covers the PixelCNN masked convolutions: 32 -> 32 channels, odd k <= 7, stride 1,
+    pad k/2, tiles of whole image rows (csrc/conv_tc.cu)."""
+    Cout, Cin, kh, kw = weight.shape
+    return (os.environ.get("LAGVAE_CONV_TC", "1") != "0" and Cout == 32 and Cin == 32 and stride == 1 and kh == kw and pad == kh // 2
+            and x.shape[-1] == 32 and bool(be.lib().lagvae_conv32_supported(x.shape[0], x.shape[1], x.shape[2], kh, kw)))
+
+
+def _split_cat32(x):
+    """fp32 [..., 32] -> bf16 [..., 64] = [hi | lo] (the operand format of the conv32 kernels)."""
+    cat = torch.empty(*x.shape[:-1], 64, dtype=torch.bfloat16, device=x.device)
+    be.check(be.lib().lagvae_split_cat32(be.ptr(x), x.numel() // 32, be.ptr(cat), _st()), "lagvae_split_cat32")
+    return cat
+
+
+class _Conv32Fn(torch.autograd.Function):
+    """k x k (masked) convolution 32 -> 32 on NHWC activations through the im2col-free tcgen05 kernels: forward and dgrad
+    multiply the live taps only; wgrad returns every tap (autograd of the reference does)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mask_mode):
+        _need_cuda(x, "conv2d")
+        x = x.contiguous()
+        B, H, W, _ = x.shape
+        k = weight.shape[2]
+        w = weight.detach().contiguous()
+        xcat = _split_cat32(x)
+        wbuf = torch.empty(be.lib().lagvae_conv32_wbuf_bytes(k, k), dtype=torch.uint8, device=x.device)
+        be.check(be.lib().lagvae_conv32_prepare_weights(be.ptr(w), k, k, mask_mode, be.ptr(wbuf), _st()), "lagvae_conv32_prepare_weights")
+        y = torch.empty(B, H, W, 32, dtype=torch.float32, device=x.device)
+        be.check(be.lib().lagvae_conv32_forward(be.ptr(xcat), be.ptr(wbuf), B, H, W, k, k, mask_mode, be.ptr(y), None, _st()),
+                 "lagvae_conv32_forward")
+        ctx.save_for_backward(xcat, wbuf)
+        ctx.geom = (B, H, W, k, mask_mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xcat, wbuf = ctx.saved_tensors
+        B, H, W, k, mask_mode = ctx.geom
+        dycat = _split_cat32(dy.contiguous())
+        dw = torch.empty(32, 32, k, k, dtype=torch.float32, device=dy.device)
+        sc = _scratch(be.lib().lagvae_conv32_wgrad_scratch_bytes(k, k), "wgrad", dy.device)
+        be.check(be.lib().lagvae_conv32_wgrad(be.ptr(dycat), be.ptr(xcat), B, H, W, k, k, be.ptr(dw), be.ptr(sc), _st()),
+                 "lagvae_conv32_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, H, W, 32, dtype=torch.float32, device=dy.device)
+            be.check(be.lib().lagvae_conv32_dgrad(be.ptr(dycat), be.ptr(wbuf), B, H, W, k, k, mask_mode, be.ptr(dx), _st()),
+                     "lagvae_conv32_dgrad")
+        return dx, dw, None
 
 
 class _BNFn(torch.autograd.Function):
@@ -278,6 +332,7 @@ class MaskedConv2d(nn.Conv2d):
     def __init__(self, mask_type, masked_channels, *args, **kwargs):
         super().__init__(*args, **kwargs)
         assert mask_type in {"A", "B"}
+        self.mask_type, self.masked_channels = mask_type, masked_channels
         self.register_buffer("mask", self.weight.data.clone())
         _, _, kH, kW = self.weight.size()
         self.mask.fill_(1)
@@ -292,6 +347,8 @@ class MaskedConv2d(nn.Conv2d):
 
     def forward(self, x):
         self.weight.data.mul_(self.mask)
+        if self.masked_channels == self.in_channels and _conv32_ok(x, self.weight, self.stride[0], self.padding[0]):
+            return _Conv32Fn.apply(x, self.weight, 1 if self.mask_type == "A" else 2)
         return _ConvFn.apply(x, self.weight, self.stride[0], self.padding[0])
 
 
