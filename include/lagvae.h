@@ -257,28 +257,45 @@ int lagvae_gemm_auto(const float* A, int64_t a_rs, int64_t a_cs, const float* B,
                      size_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Im2col-free masked convolution on tcgen05 (csrc/conv_tc.cu) — MaskedConv2d inside PixelCNNBlock
- * (dec_pixelcnn_v2.py:12-30,39-47): 32 -> 32 channels, k x k (odd, <= 7), stride 1, pad k/2, NHWC.
- * Activations are staged once per layer in the "cat" format: bf16 [B,H,W,64] = [hi(32) | lo(32)] per pixel
- * (lagvae_split_cat32, or the fused BatchNorm/ELU kernels below); shifted operand tiles are 4-D TMA boxes with
- * zero fill outside the image.  mask_mode: 0 plain, 1 mask 'A', 2 mask 'B' (all input channels masked).
- * Only live taps are multiplied in forward/dgrad; wgrad returns ALL k*k taps in the torch layout [32,32,kh,kw]
- * (autograd of the reference produces gradients for masked taps as well).
+ * Im2col-free convolutions on tcgen05 (csrc/conv_tc.cu) — the PixelCNNBlock layers (dec_pixelcnn_v2.py:32-62: 1x1 64->32,
+ * MaskedConv2d k x k 32->32 :12-30, 1x1 32->64) and the head 1x1 64->64 (:145): Cin, Cout in {32, 64}, k odd <= 7,
+ * stride 1, pad k/2, NHWC, tiles of whole image rows (H*W geometry must pass lagvae_convtc_supported).
+ * Activations are staged once per layer in the "cat" format: bf16 [B,H,W,2C] = [hi(C) | lo(C)] per pixel
+ * (lagvae_split_cat, or the fused BatchNorm/ELU kernels below); shifted operand tiles are 4-D TMA boxes with zero fill
+ * outside the image.  mask_mode: 0 plain, 1 mask 'A', 2 mask 'B' (all input channels masked).  Only live taps are
+ * multiplied in forward/dgrad; wgrad returns ALL k*k taps in the torch layout [Cout,Cin,kh,kw] (autograd of the
+ * reference produces gradients for masked taps as well).  (Cin, Cout) always name the FORWARD convolution.
  * ------------------------------------------------------------------------------------------- */
-int lagvae_conv32_supported(int B, int H, int W, int kh, int kw);
-int lagvae_split_cat32(const float* x, int64_t rows, uint16_t* cat, void* stream);
-size_t lagvae_conv32_wbuf_bytes(int kh, int kw);
-/* w: fp32 [32,32,kh,kw] (torch layout) -> bf16 forward + dgrad weight tiles in wbuf (128-B aligned). */
-int lagvae_conv32_prepare_weights(const float* w, int kh, int kw, int mask_mode, void* wbuf, void* stream);
-/* y fp32 [B,H,W,32]; stats_or_null: device double[64] receiving sum(y) | sum(y^2) per channel (zeroed inside) — the
- * batch statistics of the BatchNorm that follows the convolution, accumulated in the epilogue. */
-int lagvae_conv32_forward(const uint16_t* xcat, const void* wbuf, int B, int H, int W, int kh, int kw, int mask_mode,
-                          float* y, double* stats_or_null, void* stream);
-int lagvae_conv32_dgrad(const uint16_t* dycat, const void* wbuf, int B, int H, int W, int kh, int kw, int mask_mode,
-                        float* dx, void* stream);
-size_t lagvae_conv32_wgrad_scratch_bytes(int kh, int kw);
-int lagvae_conv32_wgrad(const uint16_t* dycat, const uint16_t* xcat, int B, int H, int W, int kh, int kw, float* dw,
-                        void* scratch, void* stream);
+int lagvae_convtc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
+/* fp32 [rows, C] -> bf16 [rows, 2C] = [hi | lo], C in {32, 64} */
+int lagvae_split_cat(const float* x, int64_t rows, int C, uint16_t* cat, void* stream);
+size_t lagvae_convtc_wbuf_bytes(int Cin, int Cout, int kh, int kw);
+/* w: fp32 [Cout,Cin,kh,kw] (torch layout) -> bf16 forward + dgrad weight tiles in wbuf (128-B aligned). */
+int lagvae_convtc_prepare_weights(const float* w, int Cout, int Cin, int kh, int kw, int mask_mode, void* wbuf, void* stream);
+/* y fp32 [B,H,W,Cout] = conv(x) (+ addend fp32 [B,H,W,Cout] when given); stats_or_null: device double[2 Cout] receiving
+ * sum(y) | sum(y^2) per channel (zeroed inside) — the batch statistics of the BatchNorm that follows, accumulated in
+ * the epilogue. */
+int lagvae_convtc_forward(const uint16_t* xcat, const void* wbuf, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                          int mask_mode, const float* addend_or_null, float* y, double* stats_or_null, void* stream);
+/* dx fp32 [B,H,W,Cin] = conv_transpose(dy) (+ addend) from dycat [B,H,W,2 Cout] */
+int lagvae_convtc_dgrad(const uint16_t* dycat, const void* wbuf, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                        int mask_mode, const float* addend_or_null, float* dx, void* stream);
+size_t lagvae_convtc_wgrad_scratch_bytes(int Cin, int Cout, int kh, int kw);
+int lagvae_convtc_wgrad(const uint16_t* dycat, const uint16_t* xcat, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                        float* dw, void* scratch, void* stream);
+
+/* Fused BatchNorm2d(train) + residual + ELU (csrc/image_fused.cu; dec_pixelcnn_v2.py:40-49,61), C in {32, 64}, R rows.
+ * forward: `stats` = double[2C] sums left by lagvae_convtc_forward; out = [ELU]( (y-mean)*invstd*gamma + beta [+ residual] )
+ * written as fp32 and/or in the cat format; save_mean/save_invstd [C] for the backward; running statistics updated as
+ * nn.BatchNorm2d does (unbiased variance).  backward: dout = gradient of `out`; the activation output is read back from
+ * fp32 or cat (needed when elu != 0); emits dy (fp32 and/or cat), the residual-branch gradient dres = dout*ELU'(out),
+ * dgamma, dbeta.  scratch: device, >= 16*C bytes. */
+int lagvae_bnact_fwd(const float* y, const double* stats, int64_t R, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, const float* residual_or_null, int elu, float* out_f32_or_null, uint16_t* out_cat_or_null,
+                     float* save_mean, float* save_invstd, float* running_mean, float* running_var, void* stream);
+int lagvae_bnact_bwd(const float* dout, const float* out_f32_or_null, const uint16_t* out_cat_or_null, const float* y, int64_t R,
+                     int C, const float* gamma, const float* save_mean, const float* save_invstd, int elu, float* dy_f32_or_null,
+                     uint16_t* dy_cat_or_null, float* dres_or_null, float* dgamma, float* dbeta, void* scratch, void* stream);
 
 /* materialise the Philox dropout keep-mask the kernels would use (tests feed it to the oracle) */
 int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep,

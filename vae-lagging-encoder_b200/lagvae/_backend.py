@@ -82,14 +82,16 @@ PROTOTYPES = {
     "lagvae_gemm_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _f, _f,
                             _vp, _vp, _i, _vp, _vp]),
     "lagvae_split_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i64, _vp]),
-    "lagvae_conv32_supported": (_i, [_i, _i, _i, _i, _i]),
-    "lagvae_split_cat32": (_i, [_vp, _i64, _vp, _vp]),
-    "lagvae_conv32_wbuf_bytes": (_sz, [_i, _i]),
-    "lagvae_conv32_prepare_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
-    "lagvae_conv32_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "lagvae_conv32_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "lagvae_conv32_wgrad_scratch_bytes": (_sz, [_i, _i]),
-    "lagvae_conv32_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lagvae_convtc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "lagvae_split_cat": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "lagvae_convtc_wbuf_bytes": (_sz, [_i, _i, _i, _i]),
+    "lagvae_convtc_prepare_weights": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lagvae_convtc_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lagvae_convtc_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lagvae_convtc_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "lagvae_convtc_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lagvae_bnact_fwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_bnact_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lagvae_dropout_mask": (_i, [_u64, _u32, _i64, _f, _vp, _vp]),
 }
 

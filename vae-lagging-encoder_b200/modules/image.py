@@ -106,13 +106,14 @@ def _conv32_ok(x, weight, stride, pad):
     pad k/2, tiles of whole image rows (csrc/conv_tc.cu)."""
     Cout, Cin, kh, kw = weight.shape
     return (os.environ.get("LAGVAE_CONV_TC", "1") != "0" and Cout == 32 and Cin == 32 and stride == 1 and kh == kw and pad == kh // 2
-            and x.shape[-1] == 32 and bool(be.lib().lagvae_conv32_supported(x.shape[0], x.shape[1], x.shape[2], kh, kw)))
+            and x.shape[-1] == 32 and bool(be.lib().lagvae_convtc_supported(x.shape[0], x.shape[1], x.shape[2], 32, 32, kh, kw)))
 
 
-def _split_cat32(x):
-    """fp32 [..., 32] -> bf16 [..., 64] = [hi | lo] (the operand format of the conv32 kernels)."""
-    cat = torch.empty(*x.shape[:-1], 64, dtype=torch.bfloat16, device=x.device)
-    be.check(be.lib().lagvae_split_cat32(be.ptr(x), x.numel() // 32, be.ptr(cat), _st()), "lagvae_split_cat32")
+def _split_cat(x):
+    """fp32 [..., C] -> bf16 [..., 2C] = [hi | lo] (the operand format of the convtc kernels), C in {32, 64}."""
+    Cc = x.shape[-1]
+    cat = torch.empty(*x.shape[:-1], 2 * Cc, dtype=torch.bfloat16, device=x.device)
+    be.check(be.lib().lagvae_split_cat(be.ptr(x), x.numel() // Cc, Cc, be.ptr(cat), _st()), "lagvae_split_cat")
     return cat
 
 
@@ -127,12 +128,12 @@ class _Conv32Fn(torch.autograd.Function):
         B, H, W, _ = x.shape
         k = weight.shape[2]
         w = weight.detach().contiguous()
-        xcat = _split_cat32(x)
-        wbuf = torch.empty(be.lib().lagvae_conv32_wbuf_bytes(k, k), dtype=torch.uint8, device=x.device)
-        be.check(be.lib().lagvae_conv32_prepare_weights(be.ptr(w), k, k, mask_mode, be.ptr(wbuf), _st()), "lagvae_conv32_prepare_weights")
+        xcat = _split_cat(x)
+        wbuf = torch.empty(be.lib().lagvae_convtc_wbuf_bytes(32, 32, k, k), dtype=torch.uint8, device=x.device)
+        be.check(be.lib().lagvae_convtc_prepare_weights(be.ptr(w), 32, 32, k, k, mask_mode, be.ptr(wbuf), _st()), "lagvae_convtc_prepare_weights")
         y = torch.empty(B, H, W, 32, dtype=torch.float32, device=x.device)
-        be.check(be.lib().lagvae_conv32_forward(be.ptr(xcat), be.ptr(wbuf), B, H, W, k, k, mask_mode, be.ptr(y), None, _st()),
-                 "lagvae_conv32_forward")
+        be.check(be.lib().lagvae_convtc_forward(be.ptr(xcat), be.ptr(wbuf), B, H, W, 32, 32, k, k, mask_mode, None, be.ptr(y), None, _st()),
+                 "lagvae_convtc_forward")
         ctx.save_for_backward(xcat, wbuf)
         ctx.geom = (B, H, W, k, mask_mode)
         return y
@@ -141,16 +142,16 @@ class _Conv32Fn(torch.autograd.Function):
     def backward(ctx, dy):
         xcat, wbuf = ctx.saved_tensors
         B, H, W, k, mask_mode = ctx.geom
-        dycat = _split_cat32(dy.contiguous())
+        dycat = _split_cat(dy.contiguous())
         dw = torch.empty(32, 32, k, k, dtype=torch.float32, device=dy.device)
-        sc = _scratch(be.lib().lagvae_conv32_wgrad_scratch_bytes(k, k), "wgrad", dy.device)
-        be.check(be.lib().lagvae_conv32_wgrad(be.ptr(dycat), be.ptr(xcat), B, H, W, k, k, be.ptr(dw), be.ptr(sc), _st()),
-                 "lagvae_conv32_wgrad")
+        sc = _scratch(be.lib().lagvae_convtc_wgrad_scratch_bytes(32, 32, k, k), "wgrad", dy.device)
+        be.check(be.lib().lagvae_convtc_wgrad(be.ptr(dycat), be.ptr(xcat), B, H, W, 32, 32, k, k, be.ptr(dw), be.ptr(sc), _st()),
+                 "lagvae_convtc_wgrad")
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, H, W, 32, dtype=torch.float32, device=dy.device)
-            be.check(be.lib().lagvae_conv32_dgrad(be.ptr(dycat), be.ptr(wbuf), B, H, W, k, k, mask_mode, be.ptr(dx), _st()),
-                     "lagvae_conv32_dgrad")
+            be.check(be.lib().lagvae_convtc_dgrad(be.ptr(dycat), be.ptr(wbuf), B, H, W, 32, 32, k, k, mask_mode, None, be.ptr(dx), _st()),
+                     "lagvae_convtc_dgrad")
         return dx, dw, None
 
 
