@@ -431,22 +431,36 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 }
 
 // dW[co, ci, ty, tx] (torch layout [Cout, Cin, kh, kw]) = sum over the S pixel partitions of the four quadrants
-// hi.hi + hi.lo + lo.hi + lo.lo of the raw accumulator of that tap
-__global__ void k_conv_wgrad_reduce(const float* __restrict__ partial, int S, int total_units, int M, int Cout, int Cin,
-                                    int ntaps, int tpg, int upg, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over (tap, co, ci)
-  if (i >= ntaps * Cout * Cin) return;
-  const int tap = i / (Cout * Cin), co = (i / Cin) % Cout, ci = i % Cin;
-  const int grp = tap / tpg, j = tap % tpg;
-  int u, cb;
-  if (Cin == 32) { u = grp * upg + (j >> 1); cb = (j & 1) * 64; }
-  else { u = grp * upg + j; cb = 0; }
+// hi.hi + hi.lo + lo.hi + lo.lo of the raw accumulator of that tap.  32 outputs x 8 partition lanes per block: the S
+// partitions are summed in a fixed order (lane-strided, then a fixed tree) -> deterministic.
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_reduce(const float* __restrict__ partial, int S, int total_units, int M, int Cout, int Cin, int ntaps, int tpg,
+                    int upg, float* __restrict__ dw) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;                        // over (tap, co, ci)
+  const bool ok = i < ntaps * Cout * Cin;
   float a = 0.f;
-  for (int s = 0; s < S; ++s) {
-    const float* P = partial + ((int64_t)s * total_units + u) * M * 128;
-    a += (P[co * 128 + cb + ci] + P[co * 128 + cb + Cin + ci]) + (P[(Cout + co) * 128 + cb + ci] + P[(Cout + co) * 128 + cb + Cin + ci]);
+  int tap = 0, co = 0, ci = 0;
+  if (ok) {
+    tap = i / (Cout * Cin); co = (i / Cin) % Cout; ci = i % Cin;
+    const int grp = tap / tpg, j = tap % tpg;
+    int u, cb;
+    if (Cin == 32) { u = grp * upg + (j >> 1); cb = (j & 1) * 64; }
+    else { u = grp * upg + j; cb = 0; }
+    for (int s = sl; s < S; s += 8) {
+      const float* P = partial + ((int64_t)s * total_units + u) * M * 128;
+      a += (P[co * 128 + cb + ci] + P[co * 128 + cb + Cin + ci]) + (P[(Cout + co) * 128 + cb + ci] + P[(Cout + co) * 128 + cb + Cin + ci]);
+    }
   }
-  dw[((int64_t)co * Cin + ci) * ntaps + tap] = a;
+  red[sl][o] = a;
+  __syncthreads();
+  if (sl == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][o];
+    dw[((int64_t)co * Cin + ci) * ntaps + tap] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -700,7 +714,7 @@ int lagvae_convtc_wgrad(const uint16_t* dycat, const uint16_t* xcat, int B, int 
   k_conv_wgrad_tc<<<ng * g.S, NTHREADS, W_SMEM, st>>>(tm_dy, tm_x, g);
   LV_LAUNCH_CHECK();
   const int n = kh * kw * Cout * Cin;
-  k_conv_wgrad_reduce<<<(int)cdiv(n, 256), 256, 0, st>>>(g.partial, g.S, ng * g.upg, 2 * Cout, Cout, Cin, kh * kw, g.tpg, g.upg, dw);
+  k_conv_wgrad_reduce<<<(int)cdiv(n, 32), 256, 0, st>>>(g.partial, g.S, ng * g.upg, 2 * Cout, Cout, Cin, kh * kw, g.tpg, g.upg, dw);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }

@@ -155,6 +155,163 @@ class _Conv32Fn(torch.autograd.Function):
         return dx, dw, None
 
 
+# ------------------------------------------------------------------------------------------------------
+# fused PixelCNN block: 3 im2col-free tcgen05 convolutions with BatchNorm statistics in their epilogues + 3 fused
+# BatchNorm/residual/ELU passes forward; 3 x (BN/ELU backward, wgrad, dgrad) backward (csrc/conv_tc.cu, image_fused.cu)
+# ------------------------------------------------------------------------------------------------------
+def _fused_ok(x, cin, cout, k, padded=False):
+    if padded and cin < 32:
+        cin = 32
+    return (os.environ.get("LAGVAE_IMAGE_FUSED", "1") != "0" and x.is_cuda and x.dim() == 4 and (padded or x.shape[-1] == cin)
+            and bool(be.lib().lagvae_convtc_supported(x.shape[0], x.shape[1], x.shape[2], cin, cout, k, k)))
+
+
+def _cat_of(x):
+    """The bf16 [hi | lo] operand copy of an fp32 NHWC activation: reuse the one its producer emitted, else split."""
+    cat = getattr(x, "_lagvae_cat", None)
+    if cat is not None and cat.shape[:-1] == x.shape[:-1] and cat.shape[-1] == 2 * x.shape[-1]:
+        return cat
+    return _split_cat(x.contiguous())
+
+
+def _wprep(w, mask_mode):
+    cout, cin, k, _ = w.shape
+    wbuf = torch.empty(be.lib().lagvae_convtc_wbuf_bytes(cin, cout, k, k), dtype=torch.uint8, device=w.device)
+    be.check(be.lib().lagvae_convtc_prepare_weights(be.ptr(w.detach().contiguous()), cout, cin, k, k, mask_mode, be.ptr(wbuf), _st()),
+             "lagvae_convtc_prepare_weights")
+    return wbuf
+
+
+def _conv_fwd(xcat, wbuf, geom, cin, cout, k, mask_mode, stats):
+    B, H, W = geom
+    y = torch.empty(B, H, W, cout, dtype=torch.float32, device=xcat.device)
+    be.check(be.lib().lagvae_convtc_forward(be.ptr(xcat), be.ptr(wbuf), B, H, W, cin, cout, k, k, mask_mode, None, be.ptr(y),
+                                            be.ptr(stats), _st()), "lagvae_convtc_forward")
+    return y
+
+
+def _conv_bwd(dycat, xcat, wbuf, geom, cin, cout, k, mask_mode, addend=None, need_dx=True):
+    """(dx fp32 [B,H,W,cin] (+ addend), dw [cout,cin,k,k]) of a convtc convolution."""
+    B, H, W = geom
+    dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=dycat.device)
+    sc = _scratch(be.lib().lagvae_convtc_wgrad_scratch_bytes(cin, cout, k, k), "wgrad", dycat.device)
+    be.check(be.lib().lagvae_convtc_wgrad(be.ptr(dycat), be.ptr(xcat), B, H, W, cin, cout, k, k, be.ptr(dw), be.ptr(sc), _st()),
+             "lagvae_convtc_wgrad")
+    dx = None
+    if need_dx:
+        dx = torch.empty(B, H, W, cin, dtype=torch.float32, device=dycat.device)
+        be.check(be.lib().lagvae_convtc_dgrad(be.ptr(dycat), be.ptr(wbuf), B, H, W, cin, cout, k, k, mask_mode, be.ptr(addend), be.ptr(dx),
+                                              _st()), "lagvae_convtc_dgrad")
+    return dx, dw
+
+
+def _bnact_fwd(y, stats, bn, residual, want_f32, want_cat):
+    """[ELU]((y - mean) * invstd * gamma + beta [+ residual]) with the batch statistics left by the convolution epilogue;
+    updates bn.running_* like nn.BatchNorm2d in train().  Returns (out fp32 | None, cat | None, save_mean, save_invstd)."""
+    Cc = y.shape[-1]
+    R = y.numel() // Cc
+    out = torch.empty_like(y) if want_f32 else None
+    cat = torch.empty(*y.shape[:-1], 2 * Cc, dtype=torch.bfloat16, device=y.device) if want_cat else None
+    sm = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    si = torch.empty_like(sm)
+    be.check(be.lib().lagvae_bnact_fwd(be.ptr(y), be.ptr(stats), R, Cc, be.ptr(bn.weight.detach()), be.ptr(bn.bias.detach()), float(bn.eps),
+                                       float(bn.momentum), be.ptr(residual), 1, be.ptr(out), be.ptr(cat), be.ptr(sm), be.ptr(si),
+                                       be.ptr(bn.running_mean), be.ptr(bn.running_var), _st()), "lagvae_bnact_fwd")
+    return out, cat, sm, si
+
+
+def _bnact_bwd(dout, out_f32, out_cat, y, gamma, sm, si, want_dres):
+    """Backward of _bnact_fwd: (dycat, dres | None, dgamma, dbeta)."""
+    Cc = y.shape[-1]
+    R = y.numel() // Cc
+    dycat = torch.empty(*y.shape[:-1], 2 * Cc, dtype=torch.bfloat16, device=y.device)
+    dres = torch.empty_like(y) if want_dres else None
+    dg = torch.empty(Cc, dtype=torch.float32, device=y.device)
+    db = torch.empty_like(dg)
+    sc = _scratch(16 * Cc + 256, "bn", y.device)
+    be.check(be.lib().lagvae_bnact_bwd(be.ptr(dout), be.ptr(out_f32), be.ptr(out_cat), be.ptr(y), R, Cc, be.ptr(gamma), be.ptr(sm), be.ptr(si), 1,
+                                       None, be.ptr(dycat), be.ptr(dres), be.ptr(dg), be.ptr(db), be.ptr(sc), _st()), "lagvae_bnact_bwd")
+    return dycat, dres, dg, db
+
+
+class _PixelBlockFn(torch.autograd.Function):
+    """out = ELU(BN3(conv1x1(ELU(BN2(maskedconv_kxk(ELU(BN1(conv1x1(x))))))) + x) — PixelCNNBlock (dec_pixelcnn_v2.py:32-62)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, mods, holder):
+        _need_cuda(x, "PixelCNNBlock")
+        x = x.contiguous()
+        conv1, bn1, conv2, bn2, conv3, bn3 = mods
+        B, H, W, C = x.shape
+        Cm, k = w1.shape[0], w2.shape[2]
+        geom = (B, H, W)
+        xcat = _cat_of(x)
+        wb1, wb2, wb3 = _wprep(w1, 0), _wprep(w2, 2), _wprep(w3, 0)
+        stats = torch.empty(3, 2 * C, dtype=torch.float64, device=x.device)
+        y1 = _conv_fwd(xcat, wb1, geom, C, Cm, 1, 0, stats[0])
+        _, a1cat, sm1, si1 = _bnact_fwd(y1, stats[0], bn1, None, False, True)
+        y2 = _conv_fwd(a1cat, wb2, geom, Cm, Cm, k, 2, stats[1])
+        _, a2cat, sm2, si2 = _bnact_fwd(y2, stats[1], bn2, None, False, True)
+        y3 = _conv_fwd(a2cat, wb3, geom, Cm, C, 1, 0, stats[2])
+        out, outcat, sm3, si3 = _bnact_fwd(y3, stats[2], bn3, x, True, True)
+        holder.append(outcat)
+        ctx.save_for_backward(xcat, y1, a1cat, y2, a2cat, y3, out, wb1, wb2, wb3, sm1, si1, sm2, si2, sm3, si3,
+                              g1.detach(), g2.detach(), g3.detach())
+        ctx.geom = (geom, C, Cm, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xcat, y1, a1cat, y2, a2cat, y3, out, wb1, wb2, wb3, sm1, si1, sm2, si2, sm3, si3, g1, g2, g3 = ctx.saved_tensors
+        geom, C, Cm, k = ctx.geom
+        dout = dout.contiguous()
+        dy3cat, dpre3, dg3, db3 = _bnact_bwd(dout, out, None, y3, g3, sm3, si3, True)
+        da2, dw3 = _conv_bwd(dy3cat, a2cat, wb3, geom, Cm, C, 1, 0)
+        dy2cat, _, dg2, db2 = _bnact_bwd(da2, None, a2cat, y2, g2, sm2, si2, False)
+        da1, dw2 = _conv_bwd(dy2cat, a1cat, wb2, geom, Cm, Cm, k, 2)
+        dy1cat, _, dg1, db1 = _bnact_bwd(da1, None, a1cat, y1, g1, sm1, si1, False)
+        dx, dw1 = _conv_bwd(dy1cat, xcat, wb1, geom, C, Cm, 1, 0, addend=dpre3)     # + the residual-branch gradient
+        return dx, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, None, None
+
+
+class _ConvBnEluFn(torch.autograd.Function):
+    """ELU(BN(conv_kxk(x))) on the convtc kernels: the head 1x1 64->64 of PixelCNNDecoderV2 (dec_pixelcnn_v2.py:145-147) and
+    the mask-A 7x7 5->64 input block (:65-85; its 5 input channels are zero-padded to one 32-channel operand chunk — the
+    mask lives in the weights, which MaskedConv2d zeroes in place before every forward)."""
+
+    @staticmethod
+    def forward(ctx, x, w, g, b, bn, holder):
+        _need_cuda(x, "conv-bn-elu")
+        B, H, W, C = x.shape
+        Co, k = w.shape[0], w.shape[2]
+        Cp = C if C in (32, 64) else 32
+        wd = w.detach()
+        if Cp != C:
+            x = torch.nn.functional.pad(x, (0, Cp - C))
+            wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, Cp - C))
+        xcat = _cat_of(x.contiguous())
+        wb = _wprep(wd, 0)
+        stats = torch.empty(2 * Co, dtype=torch.float64, device=x.device)
+        y = _conv_fwd(xcat, wb, (B, H, W), Cp, Co, k, 0, stats)
+        out, outcat, sm, si = _bnact_fwd(y, stats, bn, None, True, holder is not None)
+        if holder is not None:
+            holder.append(outcat)
+        ctx.save_for_backward(xcat, y, out, wb, sm, si, g.detach())
+        ctx.geom = ((B, H, W), C, Cp, Co, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xcat, y, out, wb, sm, si, g = ctx.saved_tensors
+        geom, C, Cp, Co, k = ctx.geom
+        dycat, _, dg, db = _bnact_bwd(dout.contiguous(), out, None, y, g, sm, si, False)
+        dx, dw = _conv_bwd(dycat, xcat, wb, geom, Cp, Co, k, 0, need_dx=ctx.needs_input_grad[0])
+        if Cp != C:
+            dx = dx[..., :C] if dx is not None else None
+            dw = dw[:, :C].contiguous()
+        return dx, dw, dg, db, None, None
+
+
 class _BNFn(torch.autograd.Function):
     """nn.BatchNorm2d (affine) on NHWC rows; train(): batch statistics + running-stat update; eval(): running stats."""
 
@@ -478,6 +635,17 @@ class PixelCNNBlock(nn.Module):
         _init_convs_and_bn(self)
 
     def forward(self, input):
+        m = self.main
+        k = m[3].kernel_size[0]
+        if self.training and m[0].out_channels == 32 and _fused_ok(input, 64, 32, 1) and k <= 7:
+            m[3].weight.data.mul_(m[3].mask)                        # dec_pixelcnn_v2.py:29
+            for bn in (m[1], m[4], m[7]):
+                bn.num_batches_tracked.add_(1)
+            holder = []
+            out = _PixelBlockFn.apply(input, m[0].weight, m[1].weight, m[1].bias, m[3].weight, m[4].weight, m[4].bias,
+                                      m[6].weight, m[7].weight, m[7].bias, (m[0], m[1], m[3], m[4], m[6], m[7]), holder)
+            out._lagvae_cat = holder[0]                             # operand copy for the next block's first convolution
+            return out
         return _EluFn.apply(self.main(input), input)                # ELU(main(x) + x)  dec_pixelcnn_v2.py:61
 
 
@@ -496,6 +664,15 @@ class MaskABlock(nn.Module):
         m.bias.data.zero_()
 
     def forward(self, input):
+        conv, bn = self.main[0], self.main[1]
+        if self.training and conv.out_channels == 64 and conv.in_channels <= 32 and conv.kernel_size[0] <= 7 \
+                and _fused_ok(input, input.shape[-1], 64, conv.kernel_size[0], padded=True):
+            conv.weight.data.mul_(conv.mask)                        # dec_pixelcnn_v2.py:29
+            bn.num_batches_tracked.add_(1)
+            holder = []
+            out = _ConvBnEluFn.apply(input, conv.weight, bn.weight, bn.bias, bn, holder)
+            out._lagvae_cat = holder[0]
+            return out
         return self.main(input)
 
 
@@ -559,10 +736,14 @@ class PixelCNNDecoderV2(DecoderBase):
         m.bias.data.zero_()
 
     def _logits(self, img_nhwc):
-        h = img_nhwc
-        for i in range(5):                                            # everything except the Sigmoid
-            h = self.main[i](h)
-        return h                                                      # [N,28,28,1]
+        h = self.main[0](img_nhwc)
+        conv, bn = self.main[1], self.main[2]
+        if self.training and conv.out_channels == 64 and _fused_ok(h, 64, 64, 1):
+            bn.num_batches_tracked.add_(1)
+            h = _ConvBnEluFn.apply(h, conv.weight, bn.weight, bn.bias, bn, None)
+        else:
+            h = self.main[3](bn(conv(h)))
+        return self.main[4](h)                                        # [N,28,28,1]; the Sigmoid is fused into the NLL kernel
 
     def forward(self, input):
         """Probabilities for an NCHW input [N, nc+fm, 28, 28] (API compatibility; the loss path uses logits)."""
