@@ -297,6 +297,30 @@ int lagvae_bnact_bwd(const float* dout, const float* out_f32_or_null, const uint
                      int C, const float* gamma, const float* save_mean, const float* save_invstd, int elu, float* dy_f32_or_null,
                      uint16_t* dy_cat_or_null, float* dres_or_null, float* dgamma, float* dbeta, void* scratch, void* stream);
 
+/* PixelCNNBlock (dec_pixelcnn_v2.py:32-62) as one call per direction (csrc/image_plan.cu): conv1x1 C->Cm, BN, ELU, masked
+ * k x k Cm->Cm (mask 'B'), BN, ELU, conv1x1 Cm->C, BN, out = ELU(. + x), training-mode BatchNorm.  `stash` (caller-owned,
+ * 256-B aligned, lagvae_pixelblock_stash_bytes) keeps what the backward needs; `scratch` (lagvae_pixelblock_scratch_bytes)
+ * is transient.  x/out fp32 [B,H,W,C]; xcat/outcat: their bf16 [hi|lo] operand copies (xcat NULL: made inside; outcat NULL:
+ * not produced).  w2 must already be masked (MaskedConv2d does it in place, :29); wgrad returns all taps. */
+typedef struct lagvae_pixelblock_dims {
+  int32_t B, H, W, C, Cm, k;
+  float eps, momentum;
+} lagvae_pixelblock_dims;
+typedef struct lagvae_pixelblock_params {
+  const float *w1, *g1, *b1, *w2, *g2, *b2, *w3, *g3, *b3;   /* conv weights (torch layout), BN weight / bias */
+  float *rm1, *rv1, *rm2, *rv2, *rm3, *rv3;                  /* BN running_mean / running_var (updated by forward) */
+} lagvae_pixelblock_params;
+typedef struct lagvae_pixelblock_grads {
+  float *dw1, *dg1, *db1, *dw2, *dg2, *db2, *dw3, *dg3, *db3;
+} lagvae_pixelblock_grads;
+size_t lagvae_pixelblock_stash_bytes(const lagvae_pixelblock_dims* d);
+size_t lagvae_pixelblock_scratch_bytes(const lagvae_pixelblock_dims* d);
+int lagvae_pixelblock_forward(const lagvae_pixelblock_dims* d, const lagvae_pixelblock_params* p, const float* x,
+                              const uint16_t* xcat_or_null, void* stash, float* out, uint16_t* outcat_or_null, void* stream);
+int lagvae_pixelblock_backward(const lagvae_pixelblock_dims* d, const lagvae_pixelblock_params* p, const float* dout, const float* out,
+                               const void* stash, const uint16_t* xcat_or_null, float* dx, const lagvae_pixelblock_grads* g,
+                               void* scratch, void* stream);
+
 /* materialise the Philox dropout keep-mask the kernels would use (tests feed it to the oracle) */
 int lagvae_dropout_mask(uint64_t seed, uint32_t stream_id, int64_t n, float p, uint8_t* out_keep,
                         void* stream);

@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(HERE, "lagvae")
 BUILD_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "liblagvae.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "lstm_tc.cu", "text_plan.cu", "image_kernels.cu", "conv_tc.cu", "image_fused.cu"]
+SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "lstm_tc.cu", "text_plan.cu", "image_kernels.cu", "conv_tc.cu", "image_fused.cu", "image_plan.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -211,6 +211,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                                              __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]),
                                              __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
         __syncwarp();
+        float4 ad[8];
+        if (g.addend) {   // all eight loads in flight before the first store (Y and addend may alias as far as nvcc knows)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), row = quad * 32 + rr;
+            ad[i] = row < nrows ? __ldg((const float4*)(g.addend + (row0 + row) * COUT + grp * 32 + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + (lane >> 3), row = quad * 32 + rr;
@@ -218,8 +226,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             float4 v = *(const float4*)(cst + rr * CSTRIDE + cc);
             const int64_t o = (row0 + row) * COUT + grp * 32 + cc;
             if (g.addend) {
-              const float4 a = *(const float4*)(g.addend + o);
-              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+              v.x += ad[i].x; v.y += ad[i].y; v.z += ad[i].z; v.w += ad[i].w;
               if (g.stats) *(float4*)(cst + rr * CSTRIDE + cc) = v;
             }
             *(float4*)(g.Y + o) = v;

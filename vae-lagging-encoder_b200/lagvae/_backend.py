@@ -30,6 +30,19 @@ class TextParams(C.Structure):
     _fields_ = [("p", C.c_void_p * NPARAM)]
 
 
+class PixelBlockDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Cm", C.c_int32), ("k", C.c_int32),
+                ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+class PixelBlockParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "g1", "b1", "w2", "g2", "b2", "w3", "g3", "b3", "rm1", "rv1", "rm2", "rv2", "rm3", "rv3")]
+
+
+class PixelBlockGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dw1", "dg1", "db1", "dw2", "dg2", "db2", "dw3", "dg3", "db3")]
+
+
 class Dropout(C.Structure):
     _fields_ = [("mode", C.c_int32), ("p_in", C.c_float), ("p_out", C.c_float),
                 ("mask_in", C.c_void_p), ("mask_out", C.c_void_p), ("seed", C.c_uint64)]
@@ -92,6 +105,11 @@ PROTOTYPES = {
     "lagvae_convtc_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lagvae_bnact_fwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lagvae_bnact_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_pixelblock_stash_bytes": (_sz, [C.POINTER(PixelBlockDims)]),
+    "lagvae_pixelblock_scratch_bytes": (_sz, [C.POINTER(PixelBlockDims)]),
+    "lagvae_pixelblock_forward": (_i, [C.POINTER(PixelBlockDims), C.POINTER(PixelBlockParams), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_pixelblock_backward": (_i, [C.POINTER(PixelBlockDims), C.POINTER(PixelBlockParams), _vp, _vp, _vp, _vp, _vp,
+                                        C.POINTER(PixelBlockGrads), _vp, _vp]),
     "lagvae_dropout_mask": (_i, [_u64, _u32, _i64, _f, _vp, _vp]),
 }
 

@@ -234,44 +234,67 @@ def _bnact_bwd(dout, out_f32, out_cat, y, gamma, sm, si, want_dres):
     return dycat, dres, dg, db
 
 
+_BLOCK_SIZES = {}
+
+
+def _block_sizes(d):
+    key = (d.B, d.H, d.W, d.C, d.Cm, d.k)
+    if key not in _BLOCK_SIZES:
+        L = be.lib()
+        _BLOCK_SIZES[key] = (int(L.lagvae_pixelblock_stash_bytes(C.byref(d))), int(L.lagvae_pixelblock_scratch_bytes(C.byref(d))))
+    return _BLOCK_SIZES[key]
+
+
 class _PixelBlockFn(torch.autograd.Function):
-    """out = ELU(BN3(conv1x1(ELU(BN2(maskedconv_kxk(ELU(BN1(conv1x1(x))))))) + x) — PixelCNNBlock (dec_pixelcnn_v2.py:32-62)."""
+    """out = ELU(BN3(conv1x1(ELU(BN2(maskedconv_kxk(ELU(BN1(conv1x1(x))))))) + x) — PixelCNNBlock (dec_pixelcnn_v2.py:32-62):
+    one C-ABI call per direction (csrc/image_plan.cu: 10 launches forward, 15 backward)."""
 
     @staticmethod
-    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, mods, holder):
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, w3, g3, b3, bns, holder):
         _need_cuda(x, "PixelCNNBlock")
         x = x.contiguous()
-        conv1, bn1, conv2, bn2, conv3, bn3 = mods
-        B, H, W, C = x.shape
-        Cm, k = w1.shape[0], w2.shape[2]
-        geom = (B, H, W)
-        xcat = _cat_of(x)
-        wb1, wb2, wb3 = _wprep(w1, 0), _wprep(w2, 2), _wprep(w3, 0)
-        stats = torch.empty(3, 2 * C, dtype=torch.float64, device=x.device)
-        y1 = _conv_fwd(xcat, wb1, geom, C, Cm, 1, 0, stats[0])
-        _, a1cat, sm1, si1 = _bnact_fwd(y1, stats[0], bn1, None, False, True)
-        y2 = _conv_fwd(a1cat, wb2, geom, Cm, Cm, k, 2, stats[1])
-        _, a2cat, sm2, si2 = _bnact_fwd(y2, stats[1], bn2, None, False, True)
-        y3 = _conv_fwd(a2cat, wb3, geom, Cm, C, 1, 0, stats[2])
-        out, outcat, sm3, si3 = _bnact_fwd(y3, stats[2], bn3, x, True, True)
+        bn1, bn2, bn3 = bns
+        B, H, W, Cc = x.shape
+        d = be.PixelBlockDims(B, H, W, Cc, w1.shape[0], w2.shape[2], float(bn1.eps), float(bn1.momentum))
+        prm = [t.detach() for t in (w1, g1, b1, w2, g2, b2, w3, g3, b3)]
+        p = be.PixelBlockParams(*[t.data_ptr() for t in prm], bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
+                                bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), bn3.running_mean.data_ptr(),
+                                bn3.running_var.data_ptr())
+        stash = torch.empty(_block_sizes(d)[0], dtype=torch.uint8, device=x.device)
+        xcat = getattr(x, "_lagvae_cat", None)
+        if xcat is not None and tuple(xcat.shape) != (B, H, W, 2 * Cc):
+            xcat = None
+        out = torch.empty_like(x)
+        outcat = torch.empty(B, H, W, 2 * Cc, dtype=torch.bfloat16, device=x.device)
+        be.check(be.lib().lagvae_pixelblock_forward(C.byref(d), C.byref(p), be.ptr(x), be.ptr(xcat), be.ptr(stash), be.ptr(out),
+                                                    be.ptr(outcat), _st()), "lagvae_pixelblock_forward")
         holder.append(outcat)
-        ctx.save_for_backward(xcat, y1, a1cat, y2, a2cat, y3, out, wb1, wb2, wb3, sm1, si1, sm2, si2, sm3, si3,
-                              g1.detach(), g2.detach(), g3.detach())
-        ctx.geom = (geom, C, Cm, k)
+        ctx.save_for_backward(out, stash, *prm, *([xcat] if xcat is not None else []))
+        ctx.d, ctx.p = d, p
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xcat, y1, a1cat, y2, a2cat, y3, out, wb1, wb2, wb3, sm1, si1, sm2, si2, sm3, si3, g1, g2, g3 = ctx.saved_tensors
-        geom, C, Cm, k = ctx.geom
+        saved = ctx.saved_tensors
+        out, stash, prm = saved[0], saved[1], saved[2:11]
+        xcat = saved[11] if len(saved) > 11 else None
+        d = ctx.d
         dout = dout.contiguous()
-        dy3cat, dpre3, dg3, db3 = _bnact_bwd(dout, out, None, y3, g3, sm3, si3, True)
-        da2, dw3 = _conv_bwd(dy3cat, a2cat, wb3, geom, Cm, C, 1, 0)
-        dy2cat, _, dg2, db2 = _bnact_bwd(da2, None, a2cat, y2, g2, sm2, si2, False)
-        da1, dw2 = _conv_bwd(dy2cat, a1cat, wb2, geom, Cm, Cm, k, 2)
-        dy1cat, _, dg1, db1 = _bnact_bwd(da1, None, a1cat, y1, g1, sm1, si1, False)
-        dx, dw1 = _conv_bwd(dy1cat, xcat, wb1, geom, C, Cm, 1, 0, addend=dpre3)     # + the residual-branch gradient
-        return dx, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, None, None
+        shapes = [prm[0].shape, prm[1].shape, prm[2].shape, prm[3].shape, prm[4].shape, prm[5].shape, prm[6].shape, prm[7].shape,
+                  prm[8].shape]
+        sizes = [int(math.prod(sh)) for sh in shapes]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 63) // 64 * 64)      # 256-B aligned segments
+        flat = torch.empty(offs[-1], dtype=torch.float32, device=dout.device)
+        views = [flat[offs[i]: offs[i] + sizes[i]].view(shapes[i]) for i in range(9)]
+        g = be.PixelBlockGrads(*[v.data_ptr() for v in views])
+        dx = torch.empty_like(out)
+        sc = _scratch(_block_sizes(d)[1] + 256, "pixelblock", dout.device)
+        scp = (sc.data_ptr() + 255) & ~255
+        be.check(be.lib().lagvae_pixelblock_backward(C.byref(d), C.byref(ctx.p), be.ptr(dout), be.ptr(out), be.ptr(stash), be.ptr(xcat),
+                                                     be.ptr(dx), C.byref(g), C.c_void_p(scp), _st()), "lagvae_pixelblock_backward")
+        return (dx, *views, None, None)
 
 
 class _ConvBnEluFn(torch.autograd.Function):
@@ -643,7 +666,7 @@ class PixelCNNBlock(nn.Module):
                 bn.num_batches_tracked.add_(1)
             holder = []
             out = _PixelBlockFn.apply(input, m[0].weight, m[1].weight, m[1].bias, m[3].weight, m[4].weight, m[4].bias,
-                                      m[6].weight, m[7].weight, m[7].bias, (m[0], m[1], m[3], m[4], m[6], m[7]), holder)
+                                      m[6].weight, m[7].weight, m[7].bias, (m[1], m[4], m[7]), holder)
             out._lagvae_cat = holder[0]                             # operand copy for the next block's first convolution
             return out
         return _EluFn.apply(self.main(input), input)                # ELU(main(x) + x)  dec_pixelcnn_v2.py:61
