@@ -420,6 +420,14 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # informational only
             line["torch_gpu_port"] = {"error": repr(ex)[:200]}
         line["cpu_baseline"] = cpu_baseline_quick()
+    if world == 1 and not args.no_image:
+        # informational: configs[3] (Omniglot ResNet encoder + PixelCNN decoder, batch 64) through the same drop-in API
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_image
+            line["image"] = bench_image.run(B=64, steps=10, warm=3, dev=dev)
+        except Exception as ex:
+            line["image"] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -434,6 +442,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the CPU / torch-GPU side baselines")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the module-API leg (profiling runs only)")
+    ap.add_argument("--no-image", dest="no_image", action="store_true", help="skip the informational image-path (configs[3]) numbers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
