@@ -25,6 +25,13 @@ def bn_train(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
     return (x - mean) / torch.sqrt(var + eps) * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
 
 
+def masked_weight(weight: Tensor, mask: Tensor) -> Tensor:
+    """MaskedConv2d.forward multiplies `weight.data` by the mask IN PLACE (dec_pixelcnn_v2.py:29) and then convolves with
+    the parameter itself: the value is w*mask but autograd sees a plain convolution, so the gradient of EVERY tap (masked
+    ones included) is non-zero.  Same value and same gradient here, without mutating the input."""
+    return weight + (weight * mask - weight).detach()
+
+
 def conv_mask(weight: Tensor, mask_type: str, masked_channels: int) -> Tensor:
     """MaskedConv2d mask (dec_pixelcnn_v2.py:16-20)."""
     m = torch.ones_like(weight)
@@ -157,7 +164,7 @@ def pixelcnn_block(p: Dict[str, Tensor], pre: str, x: Tensor, k: int) -> Tensor:
     """PixelCNNBlock.forward (dec_pixelcnn_v2.py:32-62)."""
     c = x.shape[1] // 2
     h = F.elu(bn_train(F.conv2d(x, p[pre + "main.0.weight"]), p[pre + "main.1.weight"], p[pre + "main.1.bias"]))
-    w = p[pre + "main.3.weight"] * conv_mask(p[pre + "main.3.weight"], "B", c)
+    w = masked_weight(p[pre + "main.3.weight"], conv_mask(p[pre + "main.3.weight"], "B", c))
     h = F.elu(bn_train(F.conv2d(h, w, padding=k // 2), p[pre + "main.4.weight"], p[pre + "main.4.bias"]))
     h = bn_train(F.conv2d(h, p[pre + "main.6.weight"]), p[pre + "main.7.weight"], p[pre + "main.7.bias"])
     return F.elu(h + x)
@@ -173,7 +180,7 @@ def pixelcnn_forward(p: Dict[str, Tensor], inp: Tensor) -> Tensor:
             d_in = directs.pop(0)
             h = h + pixelcnn_block(p, pre + "direct_connects.%d." % (i - 3), d_in, KS_DIRECT[i - 3])
         if i == 0:                                                            # MaskABlock (65-85)
-            w = p[pre + "main.0.main.0.weight"] * conv_mask(p[pre + "main.0.main.0.weight"], "A", 1)
+            w = masked_weight(p[pre + "main.0.main.0.weight"], conv_mask(p[pre + "main.0.main.0.weight"], "A", 1))
             h = F.elu(bn_train(F.conv2d(h, w, padding=k // 2), p[pre + "main.0.main.1.weight"], p[pre + "main.0.main.1.bias"]))
         else:
             h = pixelcnn_block(p, pre + "main.%d." % i, h, k)

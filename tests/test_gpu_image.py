@@ -92,3 +92,28 @@ def test_image_module_api_inner_step_vs_oracle():
         l2, _, _ = vae.loss(x.cuda(), 1.0)
         assert bool(torch.isfinite(l2).all()) and not l2.requires_grad
         assert isinstance(vae.calc_mi_q(x.cuda()), float)
+
+
+@pytest.mark.parametrize("B,nz", [(4, 8), (5, 32)])
+def test_image_all_gradients_vs_oracle(B, nz):
+    """Every one of the 248 gradients (masked taps included) against the image oracle on ragged batch
+    sizes (28 / 35 pixel tiles: fewer tiles than SMs, uneven wgrad partitions)."""
+    vae, p = _build(nz)
+    vae.train()
+    x = IO.make_image_batch(B, seed=5)
+    torch.manual_seed(3)
+    eps = torch.empty(B, 1, nz, device="cuda").normal_()
+    leaves = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k and "mask" not in k) for k, v in p.items()}
+    o_loss, _, _ = IO.vae_loss(leaves, x, 0.3, eps.cpu())
+    o_loss.mean().backward()
+    torch.manual_seed(3)
+    loss, _, _ = vae.loss(x.cuda(), 0.3, nsamples=1)
+    loss.mean(dim=-1).backward()
+    assert_close(loss.detach(), o_loss.detach(), 1e-4, "loss")
+    bad = []
+    for n, q in vae.named_parameters():
+        want = leaves[n].grad.double()
+        d = float((q.grad.double().cpu() - want).norm())
+        if d > 5e-3 * max(float(want.norm()), 1e-9):
+            bad.append("%s: |diff| %.3g vs |grad| %.3g" % (n, d, float(want.norm())))
+    assert not bad, "\n".join(bad[:10])
