@@ -115,3 +115,27 @@ def test_shard_bounds_cover_and_partition():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("B,chunk", [(6, 4), (5, 2), (4, 4)])
+def test_micro_batch_accumulation_equals_full_batch(B, chunk):
+    """accumulated_inner_step (batches beyond the persistent LSTM kernels' row limit run as micro-batches) against the
+    single full-batch step of the oracle: same Σloss, same clip norm of the mean gradient, same encoder update."""
+    _setup_path()
+    import lagging_oracle as O
+    from lagvae.dp import accumulated_inner_step
+    V, ni, nh, nz, T = 60, 6, 8, 2, 5
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=4))
+    params = [p[k].clone() for k in O.ALL_KEYS]
+    x = O.make_token_batch(B, T, V)
+    eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
+    n = sum(q.numel() for q in params)
+    flat, tmp = torch.zeros(n), torch.zeros(n)
+    backend = OracleBackend(eps, 0.5, 0)
+    loss_sum, norm = accumulated_inner_step(backend, params, x, flat, tmp, chunk, max_norm=0.05,
+                                            on_chunk=lambda lo: setattr(backend, "lo", lo))
+    r = O.inner_step(p, x, 0.5, eps, max_norm=0.05, update=True)
+    assert abs(loss_sum - r["loss_sum"]) <= 1e-5 * abs(r["loss_sum"])
+    assert abs(norm - r["grad_norm"]) <= 1e-5 * r["grad_norm"] and r["coef"] < 1.0
+    for k, got in zip(O.ENC_KEYS, params[:6]):
+        assert float((got - p[k]).abs().max()) <= 1e-6 * max(1.0, float(p[k].abs().max())), k

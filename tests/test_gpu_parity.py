@@ -285,3 +285,29 @@ def test_decoder_gradient_event_fires_when_decoder_grads_are_final(golden):
     eng.enable_decoder_grads_event(c["B"], x.shape[1], 1, enable=False)
     with pytest.raises(Exception):
         eng.wait_decoder_grads(c["B"], x.shape[1], 1, side)
+
+
+def test_micro_batch_accumulation_matches_fused_step(golden):
+    """lagvae.dp.accumulated_inner_step (batches beyond the persistent LSTM kernels' 256 rows run as micro-batches whose
+    gradients accumulate before ONE clip + SGD) == the fused full-batch inner step, on the CUDA back-end."""
+    from lagvae.dp import EngineBackend, accumulated_inner_step
+    g = golden("toy_eval")
+    c = case_inputs(g)
+    B = c["B"]
+    eng = _engine(c, False)
+    x, eps = c["x"].cuda(), c["eps"].cuda()
+    # reference: fused step on the whole batch (eval mode: no dropout)
+    p_full = _plist(case_params(g))
+    gw = eng.grad_workspace()
+    out_loss, sc = torch.empty(B, device="cuda"), torch.empty(4, device="cuda")
+    eng.inner_step(p_full, x, eps, c["klw"], None, gw, out_loss, sc, max_norm=0.05)
+    # micro-batches of 5 rows (ragged last chunk)
+    p_acc = _plist(case_params(g))
+    off = [0]
+    backend = EngineBackend(eng, c["klw"], lambda b: eps[off[0]: off[0] + b].contiguous(), lambda: None, overlap=False)
+    g1, g2 = eng.grad_workspace(), eng.grad_workspace()
+    loss_sum, norm = accumulated_inner_step(backend, p_acc, x, g1, g2, 5, max_norm=0.05, on_chunk=lambda lo: off.__setitem__(0, lo))
+    assert abs(loss_sum - float(sc[0])) <= 1e-5 * abs(float(sc[0]))
+    assert abs(float(norm) - float(sc[3])) <= 2e-3 * float(sc[3])       # decoder weight gradients enter the norm with one bf16 pass
+    for i, k in enumerate(O.ENC_KEYS):
+        assert_close(p_acc[i], p_full[i], 1e-4, "post-step " + k)

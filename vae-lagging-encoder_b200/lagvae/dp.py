@@ -74,6 +74,28 @@ def dp_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x_globa
     return float(loss_sum), norm
 
 
+def accumulated_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x: torch.Tensor, flat_grads: torch.Tensor,
+                           scratch_grads: torch.Tensor, max_rows: int, max_norm: float = 5.0, lr: float = 1.0, on_chunk=None):
+    """One aggressive inner step on ONE device with the batch run as micro-batches of <= max_rows rows (the persistent
+    LSTM kernels keep <= 256 batch rows on chip): every micro-batch back-propagates the upstream gradient of the GLOBAL
+    mean (1 / B), the flat gradients accumulate, then ONE clip_grad_norm_ + encoder SGD — the arithmetic of
+    dp_inner_step with the shards executed back to back instead of on different GPUs.  `on_chunk(lo)` (optional) is
+    called before each micro-batch (row offset).  Returns (Σloss, pre-clip grad norm)."""
+    n = int(x.shape[0])
+    loss_sum = None
+    for i, lo in enumerate(range(0, n, int(max_rows))):
+        if on_chunk is not None:
+            on_chunk(lo)
+        buf = flat_grads if i == 0 else scratch_grads
+        loss = backend.forward_backward(params, x[lo:lo + int(max_rows)], 1.0 / n, buf)
+        if i:
+            flat_grads.add_(scratch_grads)
+        part = loss.sum().reshape(1).to(torch.float32)
+        loss_sum = part if loss_sum is None else loss_sum + part
+    norm = backend.clip_sgd(params, flat_grads, max_norm, lr)
+    return float(loss_sum), norm
+
+
 class EngineBackend:
     """Product back-end: lagvae.TextEngine kernels; flat_grads is the engine's flat gradient workspace."""
 
@@ -110,4 +132,6 @@ class EngineBackend:
         return loss
 
     def clip_sgd(self, params, flat_grads, max_norm, lr):
+        if self._views is None or self._views[0].data_ptr() != flat_grads.data_ptr():   # e.g. after a scratch-buffer micro-batch
+            self._views = self.engine.split_grads(flat_grads)
         return self.engine.clip_sgd(params, self._views, 6, max_norm, lr, scale_all=False)
