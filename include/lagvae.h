@@ -293,6 +293,9 @@ int lagvae_convtc_wgrad(const uint16_t* dycat, const uint16_t* xcat, int B, int 
 int lagvae_bnact_fwd(const float* y, const double* stats, int64_t R, int C, const float* gamma, const float* beta, float eps,
                      float momentum, const float* residual_or_null, int elu, float* out_f32_or_null, uint16_t* out_cat_or_null,
                      float* save_mean, float* save_invstd, float* running_mean, float* running_var, void* stream);
+/* eval(): fill `stats` so that lagvae_bnact_fwd normalises with the given running statistics (pass NULL running pointers
+ * there so nothing is updated). */
+int lagvae_bn_eval_stats(const float* running_mean, const float* running_var, int64_t R, int C, double* stats, void* stream);
 int lagvae_bnact_bwd(const float* dout, const float* out_f32_or_null, const uint16_t* out_cat_or_null, const float* y, int64_t R,
                      int C, const float* gamma, const float* save_mean, const float* save_invstd, int elu, float* dy_f32_or_null,
                      uint16_t* dy_cat_or_null, float* dres_or_null, float* dgamma, float* dbeta, void* scratch, void* stream);
@@ -305,6 +308,7 @@ int lagvae_bnact_bwd(const float* dout, const float* out_f32_or_null, const uint
 typedef struct lagvae_pixelblock_dims {
   int32_t B, H, W, C, Cm, k;
   float eps, momentum;
+  int32_t eval;   /* != 0: eval() — normalise with the running statistics, update nothing (forward only) */
 } lagvae_pixelblock_dims;
 typedef struct lagvae_pixelblock_params {
   const float *w1, *g1, *b1, *w2, *g2, *b2, *w3, *g3, *b3;   /* conv weights (torch layout), BN weight / bias */

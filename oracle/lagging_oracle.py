@@ -17,7 +17,7 @@ root).  Parameter names are the reference `state_dict` keys.
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import List,  Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -287,6 +287,89 @@ def next_batch_index(rng: np.random.RandomState, nbatch: int) -> int:
 # "fast port": the same path expressed with torch.nn modules (the arithmetic library the reference
 # itself calls — SURVEY §8(c2)); used ONLY for timing the CPU baseline in bench.py.
 # ----------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------------
+# generation — host-driven token loops of dec_lstm.py:163-367, restated on the explicit cell
+# ------------------------------------------------------------------------------------------------------
+def decoder_step(p: Params, ids: Tensor, z_rows: Tensor, h: Tensor, c: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """One decoder time step on n rows (dec_lstm.py:208-216 / 291-298): logits [n, V], h', c'.  No dropout on these
+    paths (the reference applies neither dropout_in nor dropout_out while generating)."""
+    x_in = torch.cat([p["decoder.embed.weight"][ids], z_rows], dim=1)
+    a = x_in @ p["decoder.lstm.weight_ih_l0"].t() + p["decoder.lstm.bias_ih_l0"] + h @ p["decoder.lstm.weight_hh_l0"].t() \
+        + p["decoder.lstm.bias_hh_l0"]
+    i, f, g, o = a.chunk(4, dim=1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    h2 = torch.sigmoid(o) * torch.tanh(c2)
+    return h2 @ p["decoder.pred_linear.weight"].t(), h2, c2
+
+
+def decoder_init_state(p: Params, z: Tensor) -> Tuple[Tensor, Tensor]:
+    c0 = z @ p["decoder.trans_linear.weight"].t()                 # dec_lstm.py:186 / 278
+    return torch.tanh(c0), c0
+
+
+def greedy_decode(p: Params, z: Tensor, bos: int = 1, eos: int = 2, max_len: int = 100) -> List[List[int]]:
+    """LSTMDecoder.greedy_decode (dec_lstm.py:266-314) as token ids: argmax per step, a sentence keeps receiving tokens
+    until (and including) its first </s>; at most max_len - 1 steps."""
+    n = z.shape[0]
+    h, c = decoder_init_state(p, z)
+    ids = torch.full((n,), bos, dtype=torch.long)
+    alive = [True] * n
+    out: List[List[int]] = [[] for _ in range(n)]
+    steps = 1
+    while any(alive) and steps < max_len:
+        logits, h, c = decoder_step(p, ids, z, h, c)
+        ids = logits.argmax(dim=1)
+        steps += 1
+        for b in range(n):
+            if alive[b]:
+                out[b].append(int(ids[b]))
+                alive[b] = int(ids[b]) != eos
+    return out
+
+
+def beam_search_decode(p: Params, z: Tensor, K: int = 5, bos: int = 1, eos: int = 2, max_steps: int = 100) -> List[List[int]]:
+    """LSTMDecoder.beam_search_decode (dec_lstm.py:163-264), sentence by sentence: every step scores
+    (live hypotheses x V) continuations, keeps the best K - #completed, moves those ending in </s> to the completed set;
+    returns the best-scoring hypothesis including the leading <s>."""
+    V = p["decoder.pred_linear.weight"].shape[0]
+    res: List[List[int]] = []
+    h0, c0 = decoder_init_state(p, z)
+    for b in range(z.shape[0]):
+        nodes: List[Tuple[int, int]] = [(-1, bos)]            # (parent node, token)
+        live, live_lp = [0], [0.0]
+        h, c = h0[b:b + 1], c0[b:b + 1]
+        done: List[Tuple[float, int]] = []
+        t = 0
+        while len(done) < K and t < max_steps:
+            t += 1
+            ids = torch.tensor([nodes[i][1] for i in live], dtype=torch.long)
+            logits, h2, c2 = decoder_step(p, ids, z[b:b + 1].expand(len(live), -1), h, c)
+            score = torch.log_softmax(logits, dim=-1) + torch.tensor(live_lp, dtype=torch.float32).view(-1, 1)
+            top_lp, top_ix = torch.topk(score.reshape(-1), K - len(done))
+            new_live, new_lp, rows = [], [], []
+            for lp, ix in zip(top_lp.tolist(), top_ix.tolist()):
+                li, w = ix // V, ix % V
+                nodes.append((live[li], w))
+                if w == eos:
+                    done.append((lp, len(nodes) - 1))
+                else:
+                    new_live.append(len(nodes) - 1)
+                    new_lp.append(lp)
+                    rows.append(li)
+            live, live_lp = new_live, new_lp
+            if not live:
+                break
+            h, c = h2[rows], c2[rows]
+        done += list(zip(live_lp, live))
+        best = max(done, key=lambda d: d[0])[1]
+        toks = []
+        while best >= 0:
+            toks.append(nodes[best][1])
+            best = nodes[best][0]
+        res.append(toks[::-1])
+    return res
+
+
 class FastPort(torch.nn.Module):
     """Module-based port of modules/vae.py + enc_lstm.py + dec_lstm.py with the reference's own
     layer types (nn.Embedding / nn.LSTM / nn.Linear / CrossEntropyLoss) so that a CPU (or

@@ -175,6 +175,35 @@ def run_case(ref, name, V, ni, nh, nz, B, T, ns, train, klw, head_scale, out_dir
     return p0
 
 
+def run_generation_case(ref, name, V, ni, nh, nz, n, out_dir):
+    """Generation paths: the reference's greedy and beam decoders on a trained-like model against the oracle
+    restatement; writes the parameters, latents and token ids as a fixture."""
+    vae = build_reference(ref, V, ni, nh, nz, 0.5, 0.5, seed=5)
+    O.scale_trained_like({k: q for k, q in vae.named_parameters()}, 6.0)
+    with torch.no_grad():                                  # decisive, non-degenerate next-token distributions
+        vae.decoder.pred_linear.weight.mul_(6.0)
+        vae.decoder.lstm.weight_ih_l0.mul_(2.0)
+    vae.eval()
+    p0 = params_of(vae)
+    z = torch.randn(n, nz, generator=torch.Generator().manual_seed(11)) * 1.5
+    with torch.no_grad():
+        g_ref = [[int(w) for w in s] for s in vae.decode(z, "greedy")]
+        b_ref = [[int(w) for w in s] for s in vae.decode(z, "beam", K=5)]
+    g_o = O.greedy_decode(p0, z)
+    b_o = O.beam_search_decode(p0, z, 5)
+    assert g_o == g_ref, (name, "greedy", g_o[:2], g_ref[:2])
+    assert b_o == b_ref, (name, "beam", b_o[:2], b_ref[:2])
+    lens = [len(s) for s in g_ref]
+    print("[%s] greedy lengths %s, beam lengths %s: oracle == reference" % (name, lens, [len(s) for s in b_ref]))
+    assert len(set(tuple(s) for s in g_ref)) > 1 and min(lens) < 99, "degenerate generation case"
+    out = {"meta": np.array([V, ni, nh, nz, n], dtype=np.int64), "z": z.numpy(),
+           "greedy": np.array([s + [-1] * (100 - len(s)) for s in g_ref], dtype=np.int64),
+           "beam": np.array([s + [-1] * (102 - len(s)) for s in b_ref], dtype=np.int64)}
+    for k in O.ALL_KEYS:
+        out["p." + k] = p0[k].numpy()
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--yahoo", action="store_true", help="also run the Yahoo-shape KAT (slow)")
@@ -194,6 +223,7 @@ def main():
     run_case(ref, "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 3, False, 1.0, 1.5, out_dir)
     # KL ~ 0 regime at the stock init (no head scaling) — conditioning check
     run_case(ref, "toy_stockinit_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.0, out_dir)
+    run_generation_case(ref, "generation_small", 24, 16, 32, 4, 8, out_dir)
     if a.yahoo:
         # the params themselves are stored in fp16-lossless form? no: regenerated in tests via
         # O.init_text_params(seed) — so build the reference FROM oracle params here.

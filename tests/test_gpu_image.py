@@ -117,3 +117,47 @@ def test_image_all_gradients_vs_oracle(B, nz):
         if d > 5e-3 * max(float(want.norm()), 1e-9):
             bad.append("%s: |diff| %.3g vs |grad| %.3g" % (n, d, float(want.norm())))
     assert not bad, "\n".join(bad[:10])
+
+
+def test_pixelcnn_ancestral_sampling_is_causally_consistent():
+    """PixelCNNDecoderV2.decode (dec_pixelcnn_v2.py:201-232) in eval() mode: because of the causal masks the
+    probability of pixel (i, j) given the finished image equals the one it was decided from, so the deterministic decode
+    must be a fixed point: x == (p >= 0.5) at every pixel (fails if a mask leaks, or the loop order / channel is wrong)."""
+    vae, p = _build(8)
+    vae.train()
+    with torch.no_grad():                                     # warm the BatchNorm running statistics (momentum 0.1)
+        for i in range(30):
+            vae.loss(IO.make_image_batch(8, seed=40 + i).cuda(), 1.0)
+    vae.eval()
+    torch.manual_seed(4)
+    z = torch.randn(3, 8, device="cuda")
+    x, probs = vae.decoder.decode(z, True)
+    assert x.shape == (3, 1, 28, 28) and probs.shape == (3, 1, 28, 28)
+    margin = (probs - 0.5).abs() > 1e-4                       # ignore exact-threshold ties
+    assert bool(((x > 0.5) == (probs >= 0.5))[margin].all())
+    torch.manual_seed(5)
+    xs, _ = vae.decoder.decode(z, False)
+    assert set(xs.unique().tolist()) == {0.0, 1.0}                # Bernoulli draws: both values occur
+
+
+def test_image_eval_mode_fused_matches_first_tier(monkeypatch):
+    """eval() forward (BatchNorm running statistics; image.py test(), calc_mi, ancestral sampling) on the fused tcgen05
+    path against the first-tier per-layer kernels on the same model."""
+    vae, p = _build(8)
+    vae.train()
+    with torch.no_grad():
+        for i in range(5):                                    # move the running statistics away from (0, 1)
+            vae.loss(IO.make_image_batch(8, seed=60 + i).cuda(), 1.0)
+    vae.eval()
+    x = IO.make_image_batch(5, seed=7).cuda()
+    sd_before = {k: v.clone() for k, v in vae.state_dict().items()}
+    with torch.no_grad():
+        torch.manual_seed(9)
+        l_fused, r_fused, k_fused = vae.loss(x, 1.0)
+        monkeypatch.setenv("LAGVAE_IMAGE_FUSED", "0")
+        torch.manual_seed(9)
+        l_tier1, r_tier1, k_tier1 = vae.loss(x, 1.0)
+    assert_close(r_fused, r_tier1, 1e-4, "rec (eval)")
+    assert_close(l_fused, l_tier1, 1e-4, "loss (eval)")
+    for k, v in vae.state_dict().items():                    # eval() updates no statistics
+        assert torch.equal(v, sd_before[k]), k

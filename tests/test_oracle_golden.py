@@ -104,3 +104,17 @@ def test_burn_window_rule():
         if w.update(1000.0 - n, 100):
             break
     assert n == 99  # hard cap: sub_iter < 100 -> at most 99 updates (text.py:371)
+
+
+def test_generation_oracle_matches_reference_tokens(golden):
+    """Greedy and beam decoding (dec_lstm.py:163-314) of the oracle against the token ids the unmodified
+    reference produced (fixture written by oracle/validate_against_reference.py::run_generation_case)."""
+    import lagging_oracle as O
+    g = golden("generation_small")
+    p = {k: torch.from_numpy(g["p." + k]) for k in O.ALL_KEYS}
+    z = torch.from_numpy(g["z"])
+    want_g = [[int(t) for t in row if t >= 0] for row in g["greedy"]]
+    want_b = [[int(t) for t in row if t >= 0] for row in g["beam"]]
+    assert O.greedy_decode(p, z) == want_g
+    assert O.beam_search_decode(p, z, 5) == want_b
+    assert any(len(s) < 99 for s in want_g) and want_g != [s[1:] for s in want_b]      # the case is not degenerate

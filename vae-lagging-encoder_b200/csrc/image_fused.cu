@@ -176,6 +176,15 @@ k_bnact_bwd_apply(const float* __restrict__ dout, const float* __restrict__ out,
   }
 }
 
+// eval(): sums that make k_bnact_fwd reproduce the running statistics (mean = Σ/R, var = Σ²/R - mean²)
+__global__ void k_bn_eval_stats(const float* __restrict__ rm, const float* __restrict__ rv, int64_t R, int C, double* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)rm[c], v = (double)rv[c];
+  stats[c] = m * (double)R;
+  stats[C + c] = (v + m * m) * (double)R;
+}
+
 int grid_rows(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256), 148 * 8); }
 
 }  // namespace
@@ -199,6 +208,13 @@ int lagvae_bnact_fwd(const float* y, const double* stats, int64_t R, int C, cons
   else
     k_bnact_fwd<64><<<grid, 256, 0, st>>>(y, stats, R, gamma, beta, eps, momentum, residual_or_null, elu, out_f32_or_null,
                                           (__nv_bfloat16*)out_cat_or_null, save_mean, save_invstd, running_mean, running_var);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
+
+int lagvae_bn_eval_stats(const float* running_mean, const float* running_var, int64_t R, int C, double* stats, void* stream) {
+  LV_CHECK_ARG(running_mean && running_var && stats && R > 0 && C > 0, "bn_eval_stats: bad argument");
+  k_bn_eval_stats<<<(int)cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, R, C, stats);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }

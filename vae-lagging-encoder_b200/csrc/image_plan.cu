@@ -114,12 +114,21 @@ int lagvae_pixelblock_forward(const lagvae_pixelblock_dims* d, const lagvae_pixe
   LV_TRY(lagvae_convtc_prepare_weights(p->w2, Cm, Cm, k, k, 2, s.wb2, stream));
   LV_TRY(lagvae_convtc_prepare_weights(p->w3, C, Cm, 1, 1, 0, s.wb3, stream));
   double *st1 = s.stats, *st2 = s.stats + 2 * C, *st3 = s.stats + 4 * C;
-  LV_TRY(lagvae_convtc_forward(xcat, s.wb1, B, H, W, C, Cm, 1, 1, 0, nullptr, s.y1, st1, stream));
-  LV_TRY(lagvae_bnact_fwd(s.y1, st1, R, Cm, p->g1, p->b1, d->eps, d->momentum, nullptr, 1, nullptr, s.a1cat, s.sm1, s.si1, p->rm1, p->rv1, stream));
-  LV_TRY(lagvae_convtc_forward(s.a1cat, s.wb2, B, H, W, Cm, Cm, k, k, 2, nullptr, s.y2, st2, stream));
-  LV_TRY(lagvae_bnact_fwd(s.y2, st2, R, Cm, p->g2, p->b2, d->eps, d->momentum, nullptr, 1, nullptr, s.a2cat, s.sm2, s.si2, p->rm2, p->rv2, stream));
-  LV_TRY(lagvae_convtc_forward(s.a2cat, s.wb3, B, H, W, Cm, C, 1, 1, 0, nullptr, s.y3, st3, stream));
-  LV_TRY(lagvae_bnact_fwd(s.y3, st3, R, C, p->g3, p->b3, d->eps, d->momentum, x, 1, out, outcat_or_null, s.sm3, s.si3, p->rm3, p->rv3, stream));
+  const bool ev = d->eval != 0;
+  if (ev) {   // eval(): running statistics, nothing is updated (dec_pixelcnn_v2 under vae.eval())
+    LV_TRY(lagvae_bn_eval_stats(p->rm1, p->rv1, R, Cm, st1, stream));
+    LV_TRY(lagvae_bn_eval_stats(p->rm2, p->rv2, R, Cm, st2, stream));
+    LV_TRY(lagvae_bn_eval_stats(p->rm3, p->rv3, R, C, st3, stream));
+  }
+  LV_TRY(lagvae_convtc_forward(xcat, s.wb1, B, H, W, C, Cm, 1, 1, 0, nullptr, s.y1, ev ? nullptr : st1, stream));
+  LV_TRY(lagvae_bnact_fwd(s.y1, st1, R, Cm, p->g1, p->b1, d->eps, d->momentum, nullptr, 1, nullptr, s.a1cat, s.sm1, s.si1,
+                          ev ? nullptr : p->rm1, ev ? nullptr : p->rv1, stream));
+  LV_TRY(lagvae_convtc_forward(s.a1cat, s.wb2, B, H, W, Cm, Cm, k, k, 2, nullptr, s.y2, ev ? nullptr : st2, stream));
+  LV_TRY(lagvae_bnact_fwd(s.y2, st2, R, Cm, p->g2, p->b2, d->eps, d->momentum, nullptr, 1, nullptr, s.a2cat, s.sm2, s.si2,
+                          ev ? nullptr : p->rm2, ev ? nullptr : p->rv2, stream));
+  LV_TRY(lagvae_convtc_forward(s.a2cat, s.wb3, B, H, W, Cm, C, 1, 1, 0, nullptr, s.y3, ev ? nullptr : st3, stream));
+  LV_TRY(lagvae_bnact_fwd(s.y3, st3, R, C, p->g3, p->b3, d->eps, d->momentum, x, 1, out, outcat_or_null, s.sm3, s.si3,
+                          ev ? nullptr : p->rm3, ev ? nullptr : p->rv3, stream));
   return LAGVAE_OK;
 }
 
@@ -128,6 +137,7 @@ int lagvae_pixelblock_backward(const lagvae_pixelblock_dims* d, const lagvae_pix
                                void* scratch, void* stream) {
   LV_CHECK_ARG(dims_ok(d) && p && dout && out && stash && dx && g && scratch && ((uintptr_t)stash & 255) == 0 &&
                ((uintptr_t)scratch & 255) == 0, "pixelblock_backward: bad argument");
+  LV_CHECK_ARG(d->eval == 0, "pixelblock_backward: eval()-mode BatchNorm backward is not part of the path");
   const Stash s = carve_stash(d, const_cast<void*>(stash));
   const Scratch w = carve_scratch(d, scratch);
   const int B = d->B, H = d->H, W = d->W, C = d->C, Cm = d->Cm, k = d->k;

@@ -32,7 +32,7 @@ class TextParams(C.Structure):
 
 class PixelBlockDims(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("Cm", C.c_int32), ("k", C.c_int32),
-                ("eps", C.c_float), ("momentum", C.c_float)]
+                ("eps", C.c_float), ("momentum", C.c_float), ("eval", C.c_int32)]
 
 
 class PixelBlockParams(C.Structure):
@@ -104,6 +104,7 @@ PROTOTYPES = {
     "lagvae_convtc_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "lagvae_convtc_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lagvae_bnact_fwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lagvae_bn_eval_stats": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "lagvae_bnact_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lagvae_pixelblock_stash_bytes": (_sz, [C.POINTER(PixelBlockDims)]),
     "lagvae_pixelblock_scratch_bytes": (_sz, [C.POINTER(PixelBlockDims)]),

@@ -186,7 +186,7 @@ def _conv_fwd(xcat, wbuf, geom, cin, cout, k, mask_mode, stats):
     B, H, W = geom
     y = torch.empty(B, H, W, cout, dtype=torch.float32, device=xcat.device)
     be.check(be.lib().lagvae_convtc_forward(be.ptr(xcat), be.ptr(wbuf), B, H, W, cin, cout, k, k, mask_mode, None, be.ptr(y),
-                                            be.ptr(stats), _st()), "lagvae_convtc_forward")
+                                            be.ptr(stats) if stats is not None else None, _st()), "lagvae_convtc_forward")
     return y
 
 
@@ -205,18 +205,23 @@ def _conv_bwd(dycat, xcat, wbuf, geom, cin, cout, k, mask_mode, addend=None, nee
     return dx, dw
 
 
-def _bnact_fwd(y, stats, bn, residual, want_f32, want_cat):
-    """[ELU]((y - mean) * invstd * gamma + beta [+ residual]) with the batch statistics left by the convolution epilogue;
-    updates bn.running_* like nn.BatchNorm2d in train().  Returns (out fp32 | None, cat | None, save_mean, save_invstd)."""
+def _bnact_fwd(y, stats, bn, residual, want_f32, want_cat, training=True):
+    """[ELU]((y - mean) * invstd * gamma + beta [+ residual]).  train(): batch statistics left by the convolution epilogue in
+    `stats`, bn.running_* updated like nn.BatchNorm2d; eval(): the running statistics, nothing updated.
+    Returns (out fp32 | None, cat | None, save_mean, save_invstd)."""
     Cc = y.shape[-1]
     R = y.numel() // Cc
+    if not training:
+        be.check(be.lib().lagvae_bn_eval_stats(be.ptr(bn.running_mean), be.ptr(bn.running_var), R, Cc, be.ptr(stats), _st()),
+                 "lagvae_bn_eval_stats")
     out = torch.empty_like(y) if want_f32 else None
     cat = torch.empty(*y.shape[:-1], 2 * Cc, dtype=torch.bfloat16, device=y.device) if want_cat else None
     sm = torch.empty(Cc, dtype=torch.float32, device=y.device)
     si = torch.empty_like(sm)
     be.check(be.lib().lagvae_bnact_fwd(be.ptr(y), be.ptr(stats), R, Cc, be.ptr(bn.weight.detach()), be.ptr(bn.bias.detach()), float(bn.eps),
                                        float(bn.momentum), be.ptr(residual), 1, be.ptr(out), be.ptr(cat), be.ptr(sm), be.ptr(si),
-                                       be.ptr(bn.running_mean), be.ptr(bn.running_var), _st()), "lagvae_bnact_fwd")
+                                       be.ptr(bn.running_mean) if training else None, be.ptr(bn.running_var) if training else None, _st()),
+             "lagvae_bnact_fwd")
     return out, cat, sm, si
 
 
@@ -255,7 +260,7 @@ class _PixelBlockFn(torch.autograd.Function):
         x = x.contiguous()
         bn1, bn2, bn3 = bns
         B, H, W, Cc = x.shape
-        d = be.PixelBlockDims(B, H, W, Cc, w1.shape[0], w2.shape[2], float(bn1.eps), float(bn1.momentum))
+        d = be.PixelBlockDims(B, H, W, Cc, w1.shape[0], w2.shape[2], float(bn1.eps), float(bn1.momentum), 0 if bn1.training else 1)
         prm = [t.detach() for t in (w1, g1, b1, w2, g2, b2, w3, g3, b3)]
         p = be.PixelBlockParams(*[t.data_ptr() for t in prm], bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
                                 bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), bn3.running_mean.data_ptr(),
@@ -276,6 +281,8 @@ class _PixelBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         saved = ctx.saved_tensors
+        if ctx.d.eval:
+            raise LagvaeError("PixelCNNBlock backward in eval() mode is not part of the hot path")
         out, stash, prm = saved[0], saved[1], saved[2:11]
         xcat = saved[11] if len(saved) > 11 else None
         d = ctx.d
@@ -315,18 +322,21 @@ class _ConvBnEluFn(torch.autograd.Function):
         xcat = _cat_of(x.contiguous())
         wb = _wprep(wd, 0)
         stats = torch.empty(2 * Co, dtype=torch.float64, device=x.device)
-        y = _conv_fwd(xcat, wb, (B, H, W), Cp, Co, k, 0, stats)
-        out, outcat, sm, si = _bnact_fwd(y, stats, bn, None, True, holder is not None)
+        y = _conv_fwd(xcat, wb, (B, H, W), Cp, Co, k, 0, stats if bn.training else None)
+        out, outcat, sm, si = _bnact_fwd(y, stats, bn, None, True, holder is not None, training=bn.training)
         if holder is not None:
             holder.append(outcat)
         ctx.save_for_backward(xcat, y, out, wb, sm, si, g.detach())
         ctx.geom = ((B, H, W), C, Cp, Co, k)
+        ctx.training = bn.training
         return out
 
     @staticmethod
     def backward(ctx, dout):
         xcat, y, out, wb, sm, si, g = ctx.saved_tensors
         geom, C, Cp, Co, k = ctx.geom
+        if not ctx.training:
+            raise LagvaeError("BatchNorm backward in eval() mode is not part of the hot path")
         dycat, _, dg, db = _bnact_bwd(dout.contiguous(), out, None, y, g, sm, si, False)
         dx, dw = _conv_bwd(dycat, xcat, wb, geom, Cp, Co, k, 0, need_dx=ctx.needs_input_grad[0])
         if Cp != C:
@@ -660,10 +670,11 @@ class PixelCNNBlock(nn.Module):
     def forward(self, input):
         m = self.main
         k = m[3].kernel_size[0]
-        if self.training and m[0].out_channels == 32 and _fused_ok(input, 64, 32, 1) and k <= 7:
+        if (self.training or not torch.is_grad_enabled()) and m[0].out_channels == 32 and _fused_ok(input, 64, 32, 1) and k <= 7:
             m[3].weight.data.mul_(m[3].mask)                        # dec_pixelcnn_v2.py:29
-            for bn in (m[1], m[4], m[7]):
-                bn.num_batches_tracked.add_(1)
+            if self.training:
+                for bn in (m[1], m[4], m[7]):
+                    bn.num_batches_tracked.add_(1)
             holder = []
             out = _PixelBlockFn.apply(input, m[0].weight, m[1].weight, m[1].bias, m[3].weight, m[4].weight, m[4].bias,
                                       m[6].weight, m[7].weight, m[7].bias, (m[1], m[4], m[7]), holder)
@@ -688,10 +699,11 @@ class MaskABlock(nn.Module):
 
     def forward(self, input):
         conv, bn = self.main[0], self.main[1]
-        if self.training and conv.out_channels == 64 and conv.in_channels <= 32 and conv.kernel_size[0] <= 7 \
-                and _fused_ok(input, input.shape[-1], 64, conv.kernel_size[0], padded=True):
+        if (self.training or not torch.is_grad_enabled()) and conv.out_channels == 64 and conv.in_channels <= 32 \
+                and conv.kernel_size[0] <= 7 and _fused_ok(input, input.shape[-1], 64, conv.kernel_size[0], padded=True):
             conv.weight.data.mul_(conv.mask)                        # dec_pixelcnn_v2.py:29
-            bn.num_batches_tracked.add_(1)
+            if self.training:
+                bn.num_batches_tracked.add_(1)
             holder = []
             out = _ConvBnEluFn.apply(input, conv.weight, bn.weight, bn.bias, bn, holder)
             out._lagvae_cat = holder[0]
@@ -722,7 +734,7 @@ class PixelCNN(nn.Module):
 
 
 class PixelCNNDecoderV2(DecoderBase):
-    """Reference dec_pixelcnn_v2.py:123-195 (`decode` = ancestral sampling is out of scope)."""
+    """Reference dec_pixelcnn_v2.py:123-232 (training objective on the fused tcgen05 path; `decode` = ancestral sampling)."""
 
     def __init__(self, args, ngpu=1, mode="large"):
         super().__init__()
@@ -761,8 +773,9 @@ class PixelCNNDecoderV2(DecoderBase):
     def _logits(self, img_nhwc):
         h = self.main[0](img_nhwc)
         conv, bn = self.main[1], self.main[2]
-        if self.training and conv.out_channels == 64 and _fused_ok(h, 64, 64, 1):
-            bn.num_batches_tracked.add_(1)
+        if (self.training or not torch.is_grad_enabled()) and conv.out_channels == 64 and _fused_ok(h, 64, 64, 1):
+            if self.training:
+                bn.num_batches_tracked.add_(1)
             h = _ConvBnEluFn.apply(h, conv.weight, bn.weight, bn.bias, bn, None)
         else:
             h = self.main[3](bn(conv(h)))
@@ -791,4 +804,19 @@ class PixelCNNDecoderV2(DecoderBase):
         return -self.reconstruct_error(x, z)
 
     def decode(self, z, deterministic):
-        raise NotImplementedError("ancestral sampling (dec_pixelcnn_v2.py:201-232) is out of scope of the hot path (SURVEY §8 f4)")
+        """Ancestral sampling (dec_pixelcnn_v2.py:201-232): 784 sequential decoder forwards, pixel (i, j) set
+        from its predicted probability (thresholded at 0.5 or Bernoulli-sampled); returns (image [B,nc,28,28], final
+        probabilities).  Host-driven like the reference; every forward runs on the liblagvae.so kernels."""
+        _need_cuda(z, "PixelCNNDecoderV2")
+        H = W = 28
+        B = z.size(0)
+        zl = self.z_transform[0]
+        with torch.no_grad():
+            zt = _LinearFn.apply(z.detach().float().contiguous(), zl.weight, zl.bias).view(B, self.fm_latent, H, W)
+            img = torch.cat([torch.zeros(B, self.nc, H, W, dtype=torch.float32, device=z.device), zt], dim=1)
+            for i in range(H):
+                for j in range(W):
+                    probs = self.forward(img)
+                    pij = probs[:, :, i, j]
+                    img[:, :self.nc, i, j] = torch.ge(pij, 0.5).float() if deterministic else torch.bernoulli(pij)
+            return img[:, :self.nc], self.forward(img)

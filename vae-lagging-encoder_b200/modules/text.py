@@ -5,6 +5,7 @@ on the B200 kernels of liblagvae.so through lagvae.TextEngine.  nn.Embedding / n
 objects are kept only as *parameter containers* (so that `.parameters()`, `.state_dict()`,
 `.to(device)` and the stock torch optimisers behave exactly as with the reference); their forward
 methods are never called."""
+import ctypes as C
 import math
 import os
 
@@ -12,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from lagvae import DropoutSpec, LagvaeError, TextEngine
+from lagvae import _backend as be
 
 _ENGINES = {}
 _CALLS = [0]
@@ -184,10 +186,119 @@ class LSTMDecoder(DecoderBase):
         return -self.reconstruct_error(x, z)                      # dec_lstm.py:151-161
 
     def decode(self, input, z):
-        raise NotImplementedError("materialised logits are never exposed by the fused decoder; "
-                                  "use reconstruct_error / log_probability (SURVEY §8 f4: generation is out of scope)")
+        raise NotImplementedError("materialised training logits are never exposed by the fused decoder; "
+                                  "use reconstruct_error / log_probability (generation: greedy/sample/beam_search_decode)")
+
+    # ---- generation (dec_lstm.py:163-367): host-driven token loops, exactly like the reference, over ONE
+    #      decoder time step computed by liblagvae.so kernels (input projection GEMM, LSTM cell step, vocabulary projection)
+    def _init_state(self, z):
+        """(h0, c0) = (tanh(W_t z), W_t z) — dec_lstm.py:186-187."""
+        n = z.shape[0]
+        w = self.trans_linear.weight.detach()
+        c0 = torch.empty(n, self.nh, dtype=torch.float32, device=z.device)
+        L = be.lib()
+        be.check(L.lagvae_gemm_f32(be.ptr(z), self.nz, 1, be.ptr(w), self.nz, 1, be.ptr(c0), self.nh, n, self.nh, self.nz, 1.0, 0.0,
+                                   None, None, 0, _st()), "lagvae_gemm_f32")
+        return torch.tanh(c0), c0
+
+    def _step(self, ids, z_rows, h, c):
+        """One decoder time step on n rows: (logits [n, V], h', c').  No dropout (the reference applies none here)."""
+        _need_cuda_text(z_rows)
+        L = be.lib()
+        n, V = ids.shape[0], len(self.vocab)
+        kin = self.ni + self.nz
+        x_in = torch.cat([self.embed.weight.detach().index_select(0, ids), z_rows], dim=1).contiguous()
+        w_ih, w_hh = self.lstm.weight_ih_l0.detach(), self.lstm.weight_hh_l0.detach()
+        bias = (self.lstm.bias_ih_l0.detach() + self.lstm.bias_hh_l0.detach()).contiguous()
+        gates = torch.empty(n, 4 * self.nh, dtype=torch.float32, device=ids.device)
+        be.check(L.lagvae_gemm_f32(be.ptr(x_in), kin, 1, be.ptr(w_ih), kin, 1, be.ptr(gates), 4 * self.nh, n, 4 * self.nh, kin, 1.0, 0.0,
+                                   be.ptr(bias), None, 0, _st()), "lagvae_gemm_f32")
+        h2, c2 = torch.empty_like(h), torch.empty_like(c)
+        drop = be.Dropout()
+        be.check(L.lagvae_lstm_forward(0, self.nh, 1, n, be.ptr(w_hh), be.ptr(h.contiguous()), be.ptr(c.contiguous()), be.ptr(gates),
+                                       be.ptr(c2), be.ptr(h2), None, C.byref(drop), None, 0, _st()), "lagvae_lstm_forward")
+        logits = torch.empty(n, V, dtype=torch.float32, device=ids.device)
+        w_p = self.pred_linear.weight.detach()
+        be.check(L.lagvae_gemm_f32(be.ptr(h2), self.nh, 1, be.ptr(w_p), self.nh, 1, be.ptr(logits), V, n, V, self.nh, 1.0, 0.0,
+                                   None, None, 0, _st()), "lagvae_gemm_f32")
+        return logits, h2, c2
+
+    def _token_loop(self, z, pick):
+        """Shared body of greedy_decode / sample_decode (dec_lstm.py:266-367): a sentence keeps receiving words until (and
+        including) its first </s>; at most 99 steps."""
+        z = z.detach().float().contiguous()
+        n = z.shape[0]
+        h, c = self._init_state(z)
+        ids = torch.full((n,), self.vocab["<s>"], dtype=torch.long, device=z.device)
+        eos = self.vocab["</s>"]
+        alive = torch.ones(n, dtype=torch.bool, device=z.device)
+        decoded = [[] for _ in range(n)]
+        length_c = 1
+        while bool(alive.any()) and length_c < 100:
+            logits, h, c = self._step(ids, z, h, c)
+            ids = pick(logits)
+            length_c += 1
+            live, words = alive.tolist(), ids.tolist()
+            for i in range(n):
+                if live[i]:
+                    decoded[i].append(self.vocab.id2word(words[i]))
+            alive = alive & (ids != eos)
+        return decoded
+
+    def greedy_decode(self, z):
+        return self._token_loop(z, lambda logits: torch.argmax(logits, dim=1))
+
+    def sample_decode(self, z):
+        return self._token_loop(z, lambda logits: torch.multinomial(torch.softmax(logits, dim=1), num_samples=1).squeeze(1))
 
     def beam_search_decode(self, z, K=5):
-        raise NotImplementedError("generation (dec_lstm.py:163-367) is out of scope of the hot path (SURVEY §8 f4)")
+        """Beam search, sentence by sentence (dec_lstm.py:163-264): each step scores (live hypotheses x V) continuations,
+        keeps the best K - #completed, retires those ending in </s>; returns the best hypothesis incl. the leading <s>."""
+        z = z.detach().float().contiguous()
+        V, bos, eos = len(self.vocab), self.vocab["<s>"], self.vocab["</s>"]
+        h0, c0 = self._init_state(z)
+        result = []
+        for b in range(z.shape[0]):
+            nodes = [(-1, bos)]                                   # (parent node, token)
+            live, live_lp = [0], [0.0]
+            h, c = h0[b:b + 1], c0[b:b + 1]
+            done = []
+            t = 0
+            while len(done) < K and t < 100:
+                t += 1
+                ids = torch.tensor([nodes[i][1] for i in live], dtype=torch.long, device=z.device)
+                logits, h2, c2 = self._step(ids, z[b:b + 1].expand(len(live), -1).contiguous(), h, c)
+                score = torch.log_softmax(logits, dim=-1) + torch.tensor(live_lp, dtype=torch.float32, device=z.device).view(-1, 1)
+                top_lp, top_ix = torch.topk(score.reshape(-1), K - len(done))
+                new_live, new_lp, rows = [], [], []
+                for lp, ix in zip(top_lp.tolist(), top_ix.tolist()):
+                    li, w = ix // V, ix % V
+                    nodes.append((live[li], w))
+                    if w == eos:
+                        done.append((lp, len(nodes) - 1))
+                    else:
+                        new_live.append(len(nodes) - 1)
+                        new_lp.append(lp)
+                        rows.append(li)
+                live, live_lp = new_live, new_lp
+                if not live:
+                    break
+                sel = torch.tensor(rows, dtype=torch.long, device=z.device)
+                h, c = h2.index_select(0, sel), c2.index_select(0, sel)
+            done += list(zip(live_lp, live))
+            best = max(done, key=lambda d: d[0])[1]
+            words = []
+            while best >= 0:
+                words.append(self.vocab.id2word(nodes[best][1]))
+                best = nodes[best][0]
+            result.append(words[::-1])
+        return result
 
-    greedy_decode = sample_decode = beam_search_decode
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda_text(t):
+    if t.device.type != "cuda":
+        raise LagvaeError("modules.* run on a CUDA (B200) device only — no CPU fallback; got %s" % t.device)
