@@ -497,11 +497,13 @@ __global__ void k_split_cat(const float* __restrict__ x, int64_t rows, __nv_bflo
 //   K = 64, chunk 0 (x_hi):            row n: hi(Wm[n, :])                       row N + n: lo(Wm[n, :])
 //           chunk 1 (x_lo):            row n: hi(Wm[n, :])                       row N + n: 0
 __global__ void k_conv_wprep(const float* __restrict__ w, int Cout_w, int Cin_w, int kh, int kw, TapList taps, int pad,
-                             int dgrad, __nv_bfloat16* __restrict__ out) {
+                             int n_fwd, __nv_bfloat16* __restrict__ out_fwd, __nv_bfloat16* __restrict__ out_dgrad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;            // forward tiles first, then the dgrad tiles (one launch)
+  const int dgrad = i >= n_fwd;
+  if (dgrad) i -= n_fwd;
   const int N = dgrad ? Cin_w : Cout_w, K = dgrad ? Cout_w : Cin_w;
   const int chunks = K / 32;
-  const int per_item = 2 * N * 64;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over (tap, chunk, row 0..2N-1, col 0..63)
+  const int per_item = 2 * N * 64;                          // over (tap, chunk, row 0..2N-1, col 0..63)
   if (i >= taps.n * chunks * per_item) return;
   const int item = i / per_item, t = item / chunks, ch = item % chunks;
   const int row = (i % per_item) >> 6, col = i & 63;
@@ -515,7 +517,7 @@ __global__ void k_conv_wprep(const float* __restrict__ w, int Cout_w, int Cin_w,
   __nv_bfloat16 o;
   if (K == 32) o = row < N ? hi : (col < 32 ? lo : zero);
   else o = row < N ? hi : (ch == 0 ? lo : zero);
-  out[i] = o;
+  (dgrad ? out_dgrad : out_fwd)[i] = o;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -672,9 +674,7 @@ int lagvae_convtc_prepare_weights(const float* w, int Cout, int Cin, int kh, int
   __nv_bfloat16* wf = (__nv_bfloat16*)wbuf;
   __nv_bfloat16* wd = wf + fwd_tile_elems(Cin, Cout, kh * kw);
   const int nf = taps.n * (Cin / 32) * 2 * Cout * 64, nd = taps.n * (Cout / 32) * 2 * Cin * 64;
-  k_conv_wprep<<<(int)cdiv(nf, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, taps, kh / 2, 0, wf);
-  LV_LAUNCH_CHECK();
-  k_conv_wprep<<<(int)cdiv(nd, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, taps, kh / 2, 1, wd);
+  k_conv_wprep<<<(int)cdiv(nf + nd, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, taps, kh / 2, nf, wf, wd);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }
