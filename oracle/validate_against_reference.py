@@ -225,42 +225,45 @@ def main():
     run_case(ref, "toy_stockinit_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.0, out_dir)
     run_generation_case(ref, "generation_small", 24, 16, 32, 4, 8, out_dir)
     if a.yahoo:
-        # the params themselves are stored in fp16-lossless form? no: regenerated in tests via
-        # O.init_text_params(seed) — so build the reference FROM oracle params here.
-        V, ni, nh, nz, B, T = 20001, 512, 1024, 32, 32, 200
-        vae = build_reference(ref, V, ni, nh, nz, 0.5, 0.5)
-        p0 = O.init_text_params(V, ni, nh, nz, seed=0)
-        O.scale_trained_like(p0, 4.0)
-        sd = vae.state_dict()
-        sd.update(p0)
-        vae.load_state_dict(sd)
-        x = O.make_token_batch(B, T, V)
-        vae.eval()
-        torch.manual_seed(1)
-        loss, rec, kl = vae.loss(x, 0.1)
-        vae.zero_grad()
-        loss.mean(dim=-1).backward()
-        grads = {k: (q.grad.clone() if q.grad is not None else None) for k, q in zip(O.ALL_KEYS, vae.parameters())}  # clone: clip scales .grad in place
-        gn = float(torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0))
-        torch.manual_seed(1)
-        eps = torch.zeros(B, 1, nz).normal_()
-        torch.manual_seed(2)
-        mi = vae.calc_mi_q(x)
-        torch.manual_seed(2)
-        eps_mi = torch.zeros(B, 1, nz).normal_()
-        out = {"meta": np.array([V, ni, nh, nz, B, T, 1, 0], dtype=np.int64), "kl_weight": np.float64(0.1),
-               "eps": eps.numpy(), "eps_mi": eps_mi.numpy(), "loss": loss.detach().numpy(),
-               "rec": rec.detach().numpy(), "kl": kl.detach().numpy(), "mi": np.float64(mi),
-               "grad_norm": np.float64(gn)}
-        mu, lv = vae.encode_stats(x)
-        out["mu"], out["logvar"] = mu.detach().numpy(), lv.detach().numpy()
-        for k in O.ALL_KEYS:
-            g = grads[k] if grads[k] is not None else torch.zeros_like(p0[k])
-            out["gnorm." + k] = np.float64(g.double().norm())
-            out["gslice." + k] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy()
-        np.savez_compressed(os.path.join(out_dir, "yahoo_eval.npz"), **out)
-        print(f"[yahoo_eval] loss.sum={float(loss.sum()):.6f} KL.sum={float(kl.sum()):.6e} "
-              f"MI={mi:.7f} gnorm={gn:.7f}")
+        # BASELINE.json configs[1] and configs[2] at their full shapes; the parameters are regenerated in the tests from
+        # O.init_text_params(seed) (the reference is built FROM the oracle parameters here), fixtures keep fingerprints
+        run_big_case(ref, "yahoo_eval", 20001, 512, 1024, 32, 32, 200, 0.1, out_dir)
+        run_big_case(ref, "yelp_eval", 19997, 512, 1024, 32, 32, 100, 1.0, out_dir)
+
+
+def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir):
+    vae = build_reference(ref, V, ni, nh, nz, 0.5, 0.5)
+    p0 = O.init_text_params(V, ni, nh, nz, seed=0)
+    O.scale_trained_like(p0, 4.0)
+    sd = vae.state_dict()
+    sd.update(p0)
+    vae.load_state_dict(sd)
+    x = O.make_token_batch(B, T, V)
+    vae.eval()
+    torch.manual_seed(1)
+    loss, rec, kl = vae.loss(x, klw)
+    vae.zero_grad()
+    loss.mean(dim=-1).backward()
+    grads = {k: (q.grad.clone() if q.grad is not None else None) for k, q in zip(O.ALL_KEYS, vae.parameters())}  # clone: clip scales .grad in place
+    gn = float(torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0))
+    torch.manual_seed(1)
+    eps = torch.zeros(B, 1, nz).normal_()
+    torch.manual_seed(2)
+    mi = vae.calc_mi_q(x)
+    torch.manual_seed(2)
+    eps_mi = torch.zeros(B, 1, nz).normal_()
+    out = {"meta": np.array([V, ni, nh, nz, B, T, 1, 0], dtype=np.int64), "kl_weight": np.float64(klw),
+           "eps": eps.numpy(), "eps_mi": eps_mi.numpy(), "loss": loss.detach().numpy(),
+           "rec": rec.detach().numpy(), "kl": kl.detach().numpy(), "mi": np.float64(mi),
+           "grad_norm": np.float64(gn)}
+    mu, lv = vae.encode_stats(x)
+    out["mu"], out["logvar"] = mu.detach().numpy(), lv.detach().numpy()
+    for k in O.ALL_KEYS:
+        g = grads[k] if grads[k] is not None else torch.zeros_like(p0[k])
+        out["gnorm." + k] = np.float64(g.double().norm())
+        out["gslice." + k] = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].numpy()
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
+    print(f"[{name}] loss.sum={float(loss.sum()):.6f} KL.sum={float(kl.sum()):.6e} MI={mi:.7f} gnorm={gn:.7f}")
 
 
 if __name__ == "__main__":

@@ -161,3 +161,27 @@ def test_image_eval_mode_fused_matches_first_tier(monkeypatch):
     assert_close(l_fused, l_tier1, 1e-4, "loss (eval)")
     for k, v in vae.state_dict().items():                    # eval() updates no statistics
         assert torch.equal(v, sd_before[k]), k
+
+
+def test_image_full_batch_loss_and_grad_norm_vs_oracle():
+    """BASELINE.json configs[3] at its full size (Omniglot shape, batch 64, nz 32): per-image loss / rec / KL and the
+    clip norm of all gradients against the image oracle on the same draws (448 pixel tiles > #SMs: multi-wave tiles,
+    multi-block wgrad partitions)."""
+    B, nz = 64, 32
+    vae, p = _build(nz)
+    vae.train()
+    x = IO.make_image_batch(B, seed=21)
+    torch.manual_seed(6)
+    eps = torch.empty(B, 1, nz, device="cuda").normal_()
+    leaves = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k and "mask" not in k) for k, v in p.items()}
+    o_loss, o_rec, o_kl = IO.vae_loss(leaves, x, 0.1, eps.cpu())
+    o_loss.mean().backward()
+    o_norm = sum(float(v.grad.double().norm()) ** 2 for v in leaves.values() if v.grad is not None) ** 0.5
+    torch.manual_seed(6)
+    loss, rec, kl = vae.loss(x.cuda(), 0.1, nsamples=1)
+    loss.mean(dim=-1).backward()
+    assert_close(loss.detach(), o_loss.detach(), 1e-4, "loss")
+    assert_close(rec.detach(), o_rec.detach(), 1e-4, "rec")
+    assert_close(kl.detach(), o_kl.detach(), 1e-4, "kl", floor=1e-2)
+    norm = sum(float(q.grad.double().norm()) ** 2 for q in vae.parameters()) ** 0.5
+    assert abs(norm - o_norm) <= 2e-3 * o_norm, (norm, o_norm)

@@ -223,9 +223,11 @@ def test_backward_is_linear_in_upstream_gradient(golden):
 
 
 @pytest.mark.parametrize("force_simt", [False], ids=["default"])
-def test_yahoo_shape_against_reference_fingerprints(golden, force_simt):
-    """BASELINE.json config #2 shape (B=32, T=200, V=20001, ni=512, nh=1024, nz=32), eval mode."""
-    g = golden("yahoo_eval")
+@pytest.mark.parametrize("case", ["yahoo_eval", "yelp_eval"])
+def test_yahoo_shape_against_reference_fingerprints(golden, force_simt, case):
+    """BASELINE.json configs[1] (Yahoo: B=32, T=200, V=20001, kl_weight 0.1) and configs[2] (Yelp: V=19997, T=100,
+    kl_weight 1.0) at their full shapes (ni=512, nh=1024, nz=32), eval mode, against the unmodified reference."""
+    g = golden(case)
     V, ni, nh, nz, B, T, ns, _ = [int(v) for v in g["meta"]]
     p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=0), 4.0)
     import lagvae

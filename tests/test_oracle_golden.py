@@ -118,3 +118,20 @@ def test_generation_oracle_matches_reference_tokens(golden):
     assert O.greedy_decode(p, z) == want_g
     assert O.beam_search_decode(p, z, 5) == want_b
     assert any(len(s) < 99 for s in want_g) and want_g != [s[1:] for s in want_b]      # the case is not degenerate
+
+
+def test_oracle_full_shape_forward_vs_reference_fingerprints(golden):
+    """The oracle at a full BASELINE shape (configs[2], Yelp: V=19997, T=100, B=32, ni=512, nh=1024, nz=32) against the
+    outputs of the unmodified reference (forward only: loss, rec, KL, mu)."""
+    import lagging_oracle as O
+    g = golden("yelp_eval")
+    V, ni, nh, nz, B, T, ns, _ = [int(v) for v in g["meta"]]
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=0), 4.0)
+    x = O.make_token_batch(B, T, V)
+    with torch.no_grad():
+        loss, rec, kl = O.vae_loss(p, x, float(g["kl_weight"]), torch.from_numpy(g["eps"]))
+        mu, _ = O.encoder_forward(p, x)
+    assert_close(loss, g["loss"], 2e-5, "loss")
+    assert_close(rec, g["rec"], 2e-5, "rec")
+    assert_close(kl, g["kl"], 2e-5, "kl", floor=1e-2)
+    assert_close(mu, g["mu"], 2e-5, "mu", floor=1e-2)
