@@ -69,45 +69,30 @@ def run(B=64, steps=10, warm=3, graph=True, torch_port=True, dev=None):
         try:
             vae_g, e_opt, d_opt = build(True)
             allp = list(vae_g.parameters())
-            x_static = xs[0].clone()
-            s_static = torch.zeros((), device=dev)
 
-            def body():
+            def body_x(x):
                 e_opt.zero_grad(set_to_none=True)
                 d_opt.zero_grad(set_to_none=True)
-                loss, rc, kl = vae_g.loss(x_static, 0.1, nsamples=1)
-                s_static.copy_(loss.sum())
+                loss, rc, kl = vae_g.loss(x, 0.1, nsamples=1)
                 loss.mean(dim=-1).backward()
                 torch.nn.utils.clip_grad_norm_(allp, 5.0)
                 e_opt.step()
+                return loss.sum()
 
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                 # warm-up on a side stream (torch.cuda.graph recipe)
-                for _ in range(3):
-                    body()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
             lb = lagvae.launch_count()
-            with torch.cuda.graph(g):
-                body()
-            nodes = lagvae.launch_count() - lb
+            step_g = lagvae.GraphedStep(lambda x: body_x(x), {"x": xs[0]}, warmup=3)
+            nodes = (lagvae.launch_count() - lb) // 4      # 3 eager warm-up runs + the captured one
             for i in range(warm):
-                x_static.copy_(xs[i % 8])
-                g.replay()
-                s_static.item()
+                step_g(x=xs[i % 8]).item()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(steps):
-                x_static.copy_(xs[i % 8])                 # next batch (image.py:316-318)
-                g.replay()
-                s = s_static.item()                       # Σloss readback every step (image.py:306)
+                s = step_g(x=xs[i % 8]).item()            # next batch (image.py:316-318) + Σloss readback every step (:306)
             torch.cuda.synchronize()
             gv = steps / (time.perf_counter() - t0)
             out["cuda_graph"] = {"value": gv, "ms_per_step": 1e3 / gv, "lagvae_kernels_in_graph": nodes, "loss_sum": s,
                                  "algorithmic_tflops_live_tap": FLOPS_LIVE_TAP_STEP * (B / 64.0) * gv / 1e12}
-            del g, vae_g, e_opt, d_opt
+            del step_g, vae_g, e_opt, d_opt
         except Exception as ex:   # reported, never hidden
             out["cuda_graph"] = {"error": repr(ex)[:400]}
             torch.cuda.synchronize()

@@ -185,3 +185,42 @@ def test_image_full_batch_loss_and_grad_norm_vs_oracle():
     assert_close(kl.detach(), o_kl.detach(), 1e-4, "kl", floor=1e-2)
     norm = sum(float(q.grad.double().norm()) ** 2 for q in vae.parameters()) ** 0.5
     assert abs(norm - o_norm) <= 2e-3 * o_norm, (norm, o_norm)
+
+
+def test_graphed_step_equals_eager_steps():
+    """lagvae.GraphedStep (the image inner step of image.py:300-314 captured as ONE CUDA graph) against the same statements
+    run eagerly: same Σloss per step, same encoder parameters and BatchNorm running statistics afterwards."""
+    import lagvae
+    vae_a, _ = _build(8)
+    vae_b, _ = _build(8)
+    vae_a.train()
+    vae_b.train()
+    opt_a = torch.optim.Adam(vae_a.encoder.parameters(), lr=1e-3, capturable=True)
+    opt_b = torch.optim.Adam(vae_b.encoder.parameters(), lr=1e-3, capturable=True)
+    xs = [IO.make_image_batch(8, seed=80 + i).cuda() for i in range(3)]
+
+    def body(vae, opt, x):
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = vae.loss(x, 0.3, nsamples=1)
+        loss.mean(dim=-1).backward()
+        torch.nn.utils.clip_grad_norm_(list(vae.parameters()), 5.0)
+        opt.step()
+        return loss.sum()
+
+    torch.manual_seed(100)
+    for _ in range(3):                                        # mirrors the helper's three eager warm-up steps
+        body(vae_a, opt_a, xs[0])
+    torch.manual_seed(100)
+    step = lagvae.GraphedStep(lambda x: body(vae_b, opt_b, x), {"x": xs[0]}, warmup=3)
+    for i in (1, 2):
+        torch.manual_seed(200 + i)
+        sa = float(body(vae_a, opt_a, xs[i]))
+        torch.manual_seed(200 + i)
+        sb = float(step(x=xs[i]))
+        assert abs(sa - sb) <= 1e-5 * abs(sa), (i, sa, sb)
+    sd_a, sd_b = vae_a.state_dict(), vae_b.state_dict()
+    for k in sd_a:
+        if sd_a[k].dtype.is_floating_point:
+            assert_close(sd_b[k], sd_a[k], 1e-4, k, floor=1e-3)
+        else:
+            assert torch.equal(sd_a[k], sd_b[k]), k

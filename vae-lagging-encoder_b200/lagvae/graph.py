@@ -1,0 +1,40 @@
+"""One training step as ONE CUDA graph.
+
+The aggressive inner loop repeats the same statement sequence (zero_grad, `vae.loss`, backward, clip_grad_norm_, encoder
+optimizer step — text.py:373-387 / image.py:300-314) on same-shaped batches; for the image model that is ~800 kernels of a
+few microseconds each plus ~120 autograd nodes, and the eager loop is host-bound (profiles/README.md: 13.2 ms eager vs
+8.7 ms replayed).  `GraphedStep` captures the sequence once — the liblagvae.so launches go to the capturing stream like any
+torch op — and replays it per step: inputs are copied into static tensors, outputs are read from static tensors.
+
+Constraints (those of torch.cuda.graph): fixed shapes; optimizers constructed with `capturable=True`; nothing inside the
+body may synchronise (read Σloss from the returned static tensor AFTER the replay, as text.py:381 does with `.item()`)."""
+from typing import Callable, Dict, Sequence, Union
+
+import torch
+
+
+class GraphedStep:
+    def __init__(self, body: Callable[..., Union[torch.Tensor, Sequence[torch.Tensor]]], example_inputs: Dict[str, torch.Tensor],
+                 warmup: int = 3):
+        """body(**static_inputs) runs one full step and returns the tensor(s) to read back (e.g. loss.sum()).  It is run
+        `warmup` times eagerly on a side stream (allocator / lazy-init warm-up, as the torch.cuda.graph recipe asks — these
+        ARE real optimisation steps), then captured once."""
+        self.static_in = {k: v.clone() for k, v in example_inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body(**self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = body(**self.static_in)
+        self._single = isinstance(out, torch.Tensor)
+        self.static_out = [out] if self._single else list(out)
+
+    def __call__(self, **inputs: torch.Tensor):
+        for k, v in inputs.items():
+            self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out[0] if self._single else self.static_out
