@@ -88,3 +88,33 @@ def test_philox_host_device_contract():
         c = [hi1 ^ c[1] ^ k[0], lo1, hi0 ^ c[3] ^ k[1], lo0]
         k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
     assert c == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_image_geometry_queries_are_host_only():
+    """convtc / pixelblock size queries of include/lagvae.h answer without a device; unsupported geometries are refused."""
+    import ctypes as C
+    import lagvae._backend as be
+    L = be.lib()
+    assert L.lagvae_convtc_supported(64, 28, 28, 32, 32, 7, 7) == 1 and L.lagvae_convtc_supported(64, 28, 28, 64, 32, 1, 1) == 1
+    assert L.lagvae_convtc_supported(64, 28, 28, 5, 64, 7, 7) == 0 and L.lagvae_convtc_supported(64, 28, 28, 32, 32, 4, 4) == 0
+    # forward tiles: 25 live taps reserved as 49 x [64 rows x 64] bf16, dgrad the same
+    assert L.lagvae_convtc_wbuf_bytes(32, 32, 7, 7) == 2 * 49 * 64 * 64 * 2 + 256
+    d = be.PixelBlockDims(64, 28, 28, 64, 32, 7, 1e-5, 0.1, 0)
+    R = 64 * 28 * 28
+    stash = L.lagvae_pixelblock_stash_bytes(C.byref(d))
+    # y1, y2 (fp32 x 32), y3 (fp32 x 64), a1cat, a2cat (bf16 x 64), xcat (bf16 x 128) + weight tiles + statistics
+    assert stash >= R * (2 * 32 * 4 + 64 * 4 + 2 * 64 * 2 + 128 * 2) and stash < 2 * R * (2 * 32 * 4 + 64 * 4 + 2 * 64 * 2 + 128 * 2)
+    assert L.lagvae_pixelblock_scratch_bytes(C.byref(d)) > R * 64 * 4
+    bad = be.PixelBlockDims(64, 28, 28, 48, 32, 7, 1e-5, 0.1, 0)
+    assert L.lagvae_pixelblock_stash_bytes(C.byref(bad)) == 0
+
+
+def test_image_modules_refuse_cpu_tensors():
+    import lagvae
+    import modules
+    a = types.SimpleNamespace(nz=8, latent_feature_map=4, device="cpu")
+    vae = modules.VAE(modules.ResNetEncoderV2(a), modules.PixelCNNDecoderV2(a), a)
+    with pytest.raises(lagvae.LagvaeError):
+        vae.loss(torch.zeros(2, 1, 28, 28), 1.0)
+    with pytest.raises(lagvae.LagvaeError):
+        vae.decoder.decode(torch.zeros(2, 8), True)

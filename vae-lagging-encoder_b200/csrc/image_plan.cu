@@ -13,12 +13,13 @@
 namespace lagvae {
 namespace {
 
-struct Carver {
-  char* p;
+struct Carver {   // bump allocator over a caller-owned buffer; with base == nullptr it only measures
+  char* base;
+  size_t off = 0;
   template <typename T>
   T* take(size_t n) {
-    T* q = (T*)p;
-    p += round_up((int64_t)(n * sizeof(T)), 256);
+    T* q = base ? (T*)(base + off) : nullptr;
+    off += (size_t)round_up((int64_t)(n * sizeof(T)), 256);
     return q;
   }
 };
@@ -29,7 +30,7 @@ struct Stash {
   uint8_t *wb1, *wb2, *wb3;
   double* stats;   // [3][2C]
   float *sm1, *si1, *sm2, *si2, *sm3, *si3;
-  char* end;
+  size_t bytes;
 };
 Stash carve_stash(const lagvae_pixelblock_dims* d, void* base) {
   const size_t R = (size_t)d->B * d->H * d->W, C = d->C, Cm = d->Cm;
@@ -48,7 +49,7 @@ Stash carve_stash(const lagvae_pixelblock_dims* d, void* base) {
   s.sm1 = c.take<float>(Cm); s.si1 = c.take<float>(Cm);
   s.sm2 = c.take<float>(Cm); s.si2 = c.take<float>(Cm);
   s.sm3 = c.take<float>(C); s.si3 = c.take<float>(C);
-  s.end = c.p;
+  s.bytes = c.off;
   return s;
 }
 
@@ -56,7 +57,7 @@ struct Scratch {
   uint16_t *dy3cat, *dy2cat, *dy1cat;
   float *dpre3, *da2, *da1;
   void *wg, *bn;
-  char* end;
+  size_t bytes;
 };
 size_t wgrad_scratch_max(const lagvae_pixelblock_dims* d) {
   const size_t a = lagvae_convtc_wgrad_scratch_bytes(d->C, d->Cm, 1, 1), b = lagvae_convtc_wgrad_scratch_bytes(d->Cm, d->Cm, d->k, d->k),
@@ -75,7 +76,7 @@ Scratch carve_scratch(const lagvae_pixelblock_dims* d, void* base) {
   s.da1 = c.take<float>(R * Cm);
   s.wg = c.take<uint8_t>(wgrad_scratch_max(d));
   s.bn = c.take<uint8_t>(16 * C + 256);
-  s.end = c.p;
+  s.bytes = c.off;
   return s;
 }
 bool dims_ok(const lagvae_pixelblock_dims* d) {
@@ -92,11 +93,11 @@ extern "C" {
 
 size_t lagvae_pixelblock_stash_bytes(const lagvae_pixelblock_dims* d) {
   if (!dims_ok(d)) return 0;
-  return (size_t)(carve_stash(d, nullptr).end - (char*)nullptr) + 256;
+  return carve_stash(d, nullptr).bytes + 256;
 }
 size_t lagvae_pixelblock_scratch_bytes(const lagvae_pixelblock_dims* d) {
   if (!dims_ok(d)) return 0;
-  return (size_t)(carve_scratch(d, nullptr).end - (char*)nullptr) + 256;
+  return carve_scratch(d, nullptr).bytes + 256;
 }
 
 int lagvae_pixelblock_forward(const lagvae_pixelblock_dims* d, const lagvae_pixelblock_params* p, const float* x,
