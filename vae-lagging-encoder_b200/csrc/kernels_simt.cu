@@ -418,9 +418,16 @@ int dc0_total(const float* dc_init, const float* dh_init, const float* h0, float
 __global__ void k_time_sum(const float* __restrict__ src, int Tn, int Bd, int ncol, float* __restrict__ out) {
   const int64_t n = (int64_t)Bd * ncol;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float a = 0.f;
-    for (int t = 0; t < Tn; ++t) a += src[(int64_t)t * n + i];
-    out[i] = a;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains: the loop is load-latency bound
+    int t = 0;
+    for (; t + 4 <= Tn; t += 4) {
+      a0 += src[(int64_t)t * n + i];
+      a1 += src[(int64_t)(t + 1) * n + i];
+      a2 += src[(int64_t)(t + 2) * n + i];
+      a3 += src[(int64_t)(t + 3) * n + i];
+    }
+    for (; t < Tn; ++t) a0 += src[(int64_t)t * n + i];
+    out[i] = (a0 + a1) + (a2 + a3);
   }
 }
 int time_sum(const float* src, int Tn, int Bd, int ncol, float* out, cudaStream_t st) {
@@ -708,8 +715,25 @@ k_clip_sgd(SegTable tb, const float* __restrict__ coef_p, float lr, int scale_al
     float* p = tb.p[s];
     const int64_t n = tb.n[s];
     const bool upd = s < tb.nupd;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const float gc = g[i] * coef;   // clip_grad_norm_ multiplies even when coef == 1
+    int64_t done = 0;
+    if (((((uintptr_t)g) | ((uintptr_t)p)) & 15) == 0) {      // 16-byte vector body (pure HBM traffic: g r/w, p r/w)
+      const int64_t n4 = n >> 2;
+      float4* g4 = (float4*)g;
+      float4* p4 = (float4*)p;
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 gv = g4[i];
+        gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;   // clip_grad_norm_ multiplies even when coef == 1
+        g4[i] = gv;
+        if (upd) {
+          float4 pv = p4[i];
+          pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
+          p4[i] = pv;
+        }
+      }
+      done = n4 << 2;
+    }
+    for (int64_t i = done + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float gc = g[i] * coef;
       g[i] = gc;
       if (upd) p[i] = p[i] - lr * gc;
     }
