@@ -287,6 +287,25 @@ def next_batch_index(rng: np.random.RandomState, nbatch: int) -> int:
 # "fast port": the same path expressed with torch.nn modules (the arithmetic library the reference
 # itself calls — SURVEY §8(c2)); used ONLY for timing the CPU baseline in bench.py.
 # ----------------------------------------------------------------------------------------------
+def nll_iw(p: Params, x: Tensor, eps_chunks: List[Tensor]) -> Tensor:
+    """VAE.nll_iw (modules/vae.py:100-129): importance-weighted estimate of -log p(x), [B].  eps_chunks =
+    the successive N(0,1) draws [B, ns, nz] of encoder.sample (encoder.py:59-79), one per chunk of ns samples; weights
+    log p(z) + log p(x|z) - log q(z|x) (vae.py:147-168, encoder.py:81-109), log-sum-exp over all samples - log(nsamples)."""
+    mu, logvar = encoder_forward(p, x)
+    nz = mu.shape[1]
+    parts = []
+    for eps in eps_chunks:
+        z = reparameterize(mu, logvar, eps)                                   # [B, ns, nz]
+        log_prior = (-0.5 * z.pow(2) - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+        log_lik = -decoder_reconstruct_error(p, x, z)                         # [B, ns]
+        dev = z - mu.unsqueeze(1)
+        log_q = -0.5 * (dev.pow(2) / logvar.exp().unsqueeze(1)).sum(dim=-1) \
+            - 0.5 * (nz * math.log(2 * math.pi) + logvar.sum(dim=-1, keepdim=True))
+        parts.append(log_prior + log_lik - log_q)
+    w = torch.cat(parts, dim=-1)
+    return -(torch.logsumexp(w, dim=-1) - math.log(w.shape[-1]))
+
+
 # ------------------------------------------------------------------------------------------------------
 # generation (SURVEY §8 f4) — host-driven token loops of dec_lstm.py:163-367, restated on the explicit cell
 # ------------------------------------------------------------------------------------------------------

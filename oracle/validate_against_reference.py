@@ -175,6 +175,31 @@ def run_case(ref, name, V, ni, nh, nz, B, T, ns, train, klw, head_scale, out_dir
     return p0
 
 
+def run_nll_iw_case(ref, name, base, V, ni, nh, nz, B, T, nsamples, ns, out_dir):
+    """Evaluation path: the reference's VAE.nll_iw in eval() mode against the oracle restatement, on the
+    parameters / tokens of the fixture `base` (run_case with the same arguments rebuilds them); stores draws + result."""
+    vae = build_reference(ref, V, ni, nh, nz, 0.5, 0.5)
+    scale_head(vae, 1.5)
+    p0 = params_of(vae)
+    x = O.make_token_batch(B, T, V)
+    vae.eval()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        want = vae.nll_iw(x, nsamples, ns=ns)
+    torch.manual_seed(7)
+    chunks = [torch.zeros(B, ns, nz).normal_() for _ in range(nsamples // ns)]       # encoder.py:77, one draw per chunk
+    with torch.no_grad():
+        got = O.nll_iw(p0, x, chunks)
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-6, (name, err)
+    g = dict(np.load(os.path.join(out_dir, base + ".npz")))
+    assert np.array_equal(g["x"], x.numpy()) and all(np.array_equal(g["p." + k], p0[k].numpy()) for k in O.ALL_KEYS), \
+        "nll_iw case must share parameters and tokens with " + base
+    print("[%s] nll_iw mean %.6f (oracle rel err %.1e)" % (name, float(want.mean()), err))
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), base=np.array(base), nll=want.numpy(),
+                        eps=np.stack([c.numpy() for c in chunks]), ns=np.int64(ns))
+
+
 def run_generation_case(ref, name, V, ni, nh, nz, n, out_dir):
     """Generation paths: the reference's greedy and beam decoders on a trained-like model against the oracle
     restatement; writes the parameters, latents and token ids as a fixture."""
@@ -224,6 +249,7 @@ def main():
     # KL ~ 0 regime at the stock init (no head scaling) — conditioning check
     run_case(ref, "toy_stockinit_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.0, out_dir)
     run_generation_case(ref, "generation_small", 24, 16, 32, 4, 8, out_dir)
+    run_nll_iw_case(ref, "aligned_nll_iw", "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 6, 3, out_dir)
     if a.yahoo:
         # BASELINE.json configs[1] and configs[2] at their full shapes; the parameters are regenerated in the tests from
         # O.init_text_params(seed) (the reference is built FROM the oracle parameters here), fixtures keep fingerprints

@@ -344,3 +344,24 @@ def test_generation_matches_reference_tokens(golden):
             assert "2" not in s[:-1]
         with pytest.raises(ValueError):
             vae.decode(z, "nucleus")
+
+
+def test_nll_iw_matches_reference(golden, monkeypatch):
+    """VAE.nll_iw through the drop-in modules (encoder forward, multi-sample decoder likelihood, log q(z|x),
+    log-sum-exp) against the unmodified reference's value, with the reference's N(0,1) draws injected."""
+    import modules
+    g2 = golden("aligned_nll_iw")
+    g = golden(str(g2["base"]))
+    c = case_inputs(g)
+    vae = _build_modules(c, case_params(g)).eval()
+    chunks = [torch.from_numpy(e).cuda() for e in g2["eps"]]
+
+    def replay(self, mu, logvar, nsamples=1):          # encoder.py:59-79 with the draw of :77 replayed
+        eps = chunks.pop(0)
+        assert eps.shape == (mu.shape[0], nsamples, mu.shape[1])
+        return mu.unsqueeze(1) + eps * (0.5 * logvar).exp().unsqueeze(1)
+    monkeypatch.setattr(modules.text.GaussianEncoderBase, "reparameterize", replay)
+    with torch.no_grad():
+        nll = vae.nll_iw(c["x"].cuda(), nsamples=len(g2["eps"]) * int(g2["ns"]), ns=int(g2["ns"]))
+    assert not chunks
+    assert_close(nll, g2["nll"], OUT_TOL, "nll_iw")

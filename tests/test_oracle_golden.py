@@ -135,3 +135,15 @@ def test_oracle_full_shape_forward_vs_reference_fingerprints(golden):
     assert_close(rec, g["rec"], 2e-5, "rec")
     assert_close(kl, g["kl"], 2e-5, "kl", floor=1e-2)
     assert_close(mu, g["mu"], 2e-5, "mu", floor=1e-2)
+
+
+def test_nll_iw_oracle_matches_reference(golden):
+    """Importance-weighted NLL (vae.py:100-129) of the oracle against the unmodified reference's value."""
+    import lagging_oracle as O
+    g2 = golden("aligned_nll_iw")
+    g = golden(str(g2["base"]))
+    p = case_params(g)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        nll = O.nll_iw(p, x, [torch.from_numpy(e) for e in g2["eps"]])
+    assert_close(nll, g2["nll"], 1e-6, "nll_iw")
