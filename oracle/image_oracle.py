@@ -25,6 +25,15 @@ def bn_train(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
     return (x - mean) / torch.sqrt(var + eps) * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
 
 
+def bn(p: Dict[str, Tensor], pre: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm2d named `pre` (keys pre + weight / bias / running_mean / running_var).  train(): batch statistics
+    (bn_train); eval(): the running statistics — selected by p["__eval__"] (absent = train, the aggressive-loop case)."""
+    if not p.get("__eval__", False):
+        return bn_train(x, p[pre + "weight"], p[pre + "bias"], eps)
+    m, v = p[pre + "running_mean"].view(1, -1, 1, 1), p[pre + "running_var"].view(1, -1, 1, 1)
+    return (x - m) / torch.sqrt(v + eps) * p[pre + "weight"].view(1, -1, 1, 1) + p[pre + "bias"].view(1, -1, 1, 1)
+
+
 def masked_weight(weight: Tensor, mask: Tensor) -> Tensor:
     """MaskedConv2d.forward multiplies `weight.data` by the mask IN PLACE (dec_pixelcnn_v2.py:29) and then convolves with
     the parameter itself: the value is w*mask but autograd sees a plain convolution, so the gradient of EVERY tap (masked
@@ -139,10 +148,9 @@ def make_image_batch(B: int, seed: int = 1234) -> Tensor:
 # ------------------------------------------------------------------------------------------------------
 def resnet_block(p: Dict[str, Tensor], pre: str, x: Tensor, stride: int) -> Tensor:
     """ResNetBlock.forward (enc_resnet_v2.py:55-71); downsample branch always present here (stride 2)."""
-    res = bn_train(F.conv2d(x, p[pre + "downsample.0.weight"], stride=stride), p[pre + "downsample.1.weight"],
-                   p[pre + "downsample.1.bias"])
-    out = F.elu(bn_train(F.conv2d(x, p[pre + "conv1.weight"], stride=stride, padding=1), p[pre + "bn1.weight"], p[pre + "bn1.bias"]))
-    out = bn_train(F.conv2d(out, p[pre + "conv2.weight"], padding=1), p[pre + "bn2.weight"], p[pre + "bn2.bias"])
+    res = bn(p, pre + "downsample.1.", F.conv2d(x, p[pre + "downsample.0.weight"], stride=stride))
+    out = F.elu(bn(p, pre + "bn1.", F.conv2d(x, p[pre + "conv1.weight"], stride=stride, padding=1)))
+    out = bn(p, pre + "bn2.", F.conv2d(out, p[pre + "conv2.weight"], padding=1))
     return F.elu(out + res)
 
 
@@ -151,7 +159,7 @@ def encoder_forward(p: Dict[str, Tensor], x: Tensor) -> Tuple[Tensor, Tensor]:
     h = x
     for i in range(3):
         h = resnet_block(p, "encoder.main.0.main.%d." % i, h, 2)
-    h = F.elu(bn_train(F.conv2d(h, p["encoder.main.1.weight"]), p["encoder.main.2.weight"], p["encoder.main.2.bias"]))
+    h = F.elu(bn(p, "encoder.main.2.", F.conv2d(h, p["encoder.main.1.weight"])))
     out = h.view(h.shape[0], -1) @ p["encoder.linear.weight"].t() + p["encoder.linear.bias"]
     nz = out.shape[1] // 2
     return out[:, :nz], out[:, nz:]
@@ -163,10 +171,10 @@ def encoder_forward(p: Dict[str, Tensor], x: Tensor) -> Tuple[Tensor, Tensor]:
 def pixelcnn_block(p: Dict[str, Tensor], pre: str, x: Tensor, k: int) -> Tensor:
     """PixelCNNBlock.forward (dec_pixelcnn_v2.py:32-62)."""
     c = x.shape[1] // 2
-    h = F.elu(bn_train(F.conv2d(x, p[pre + "main.0.weight"]), p[pre + "main.1.weight"], p[pre + "main.1.bias"]))
+    h = F.elu(bn(p, pre + "main.1.", F.conv2d(x, p[pre + "main.0.weight"])))
     w = masked_weight(p[pre + "main.3.weight"], conv_mask(p[pre + "main.3.weight"], "B", c))
-    h = F.elu(bn_train(F.conv2d(h, w, padding=k // 2), p[pre + "main.4.weight"], p[pre + "main.4.bias"]))
-    h = bn_train(F.conv2d(h, p[pre + "main.6.weight"]), p[pre + "main.7.weight"], p[pre + "main.7.bias"])
+    h = F.elu(bn(p, pre + "main.4.", F.conv2d(h, w, padding=k // 2)))
+    h = bn(p, pre + "main.7.", F.conv2d(h, p[pre + "main.6.weight"]))
     return F.elu(h + x)
 
 
@@ -181,12 +189,12 @@ def pixelcnn_forward(p: Dict[str, Tensor], inp: Tensor) -> Tensor:
             h = h + pixelcnn_block(p, pre + "direct_connects.%d." % (i - 3), d_in, KS_DIRECT[i - 3])
         if i == 0:                                                            # MaskABlock (65-85)
             w = masked_weight(p[pre + "main.0.main.0.weight"], conv_mask(p[pre + "main.0.main.0.weight"], "A", 1))
-            h = F.elu(bn_train(F.conv2d(h, w, padding=k // 2), p[pre + "main.0.main.1.weight"], p[pre + "main.0.main.1.bias"]))
+            h = F.elu(bn(p, pre + "main.0.main.1.", F.conv2d(h, w, padding=k // 2)))
         else:
             h = pixelcnn_block(p, pre + "main.%d." % i, h, k)
         directs.append(h)
     h = h + pixelcnn_block(p, pre + "direct_connects.%d." % (len(KS_DIRECT) - 1), directs.pop(0), KS_DIRECT[-1])
-    h = F.elu(bn_train(F.conv2d(h, p["decoder.main.1.weight"]), p["decoder.main.2.weight"], p["decoder.main.2.bias"]))
+    h = F.elu(bn(p, "decoder.main.2.", F.conv2d(h, p["decoder.main.1.weight"])))
     return torch.sigmoid(F.conv2d(h, p["decoder.main.4.weight"]))
 
 
@@ -201,8 +209,12 @@ def decoder_reconstruct_error(p: Dict[str, Tensor], x: Tensor, z: Tensor, fm: in
     return -bce.sum(dim=2)
 
 
-def vae_loss(p: Dict[str, Tensor], x: Tensor, kl_weight: float, eps: Tensor, fm: int = 4):
-    """VAE.loss (modules/vae.py:79-98) for the image model; eps [B,ns,nz]."""
+def vae_loss(p: Dict[str, Tensor], x: Tensor, kl_weight: float, eps: Tensor, fm: int = 4, training: bool = True):
+    """VAE.loss (modules/vae.py:79-98) for the image model; eps [B,ns,nz].  training=False: eval() — every BatchNorm
+    normalises with its running statistics (image.py test() / calc_mi / sampling)."""
+    if not training:
+        p = dict(p)
+        p["__eval__"] = True
     mu, logvar = encoder_forward(p, x)
     z = mu.unsqueeze(1) + eps * (0.5 * logvar).exp().unsqueeze(1)
     KL = 0.5 * (mu.pow(2) + logvar.exp() - logvar - 1).sum(dim=1)

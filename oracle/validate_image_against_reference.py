@@ -73,12 +73,45 @@ def run_case(ref, name, B, nz, ns, klw, out_dir):
     np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
 
 
+def run_eval_case(ref, name, B, nz, ns, klw, out_dir):
+    """eval() forward (image.py test(), MI, ancestral sampling): BatchNorm normalises with its running statistics.  The
+    statistics are moved away from (0, 1) by a few train()-mode forwards of the reference, stored in the fixture, and the
+    reference's eval() loss is compared with the oracle's (training=False)."""
+    vae = build(ref, nz)
+    vae.load_state_dict(IO.init_image_params(nz, seed=0))
+    vae.train()
+    with torch.no_grad():
+        for i in range(4):
+            vae.loss(IO.make_image_batch(8, seed=300 + i), 1.0)
+    vae.eval()
+    sd = {k: v.clone() for k, v in vae.state_dict().items()}
+    x = IO.make_image_batch(B, seed=77)
+    torch.manual_seed(1)
+    with torch.no_grad():
+        loss, rec, kl = vae.loss(x, klw, nsamples=ns)
+    torch.manual_seed(1)
+    eps = torch.zeros(B, ns, nz).normal_()
+    with torch.no_grad():
+        o_loss, o_rec, o_kl = IO.vae_loss(sd, x, klw, eps, training=False)
+    err = float((o_loss - loss).abs().max() / loss.abs().max())
+    assert err < 2e-5, (name, err)
+    assert float((o_kl - kl).abs().max()) < 1e-5 * max(1.0, float(kl.abs().max()))
+    print("[%s] eval loss.sum=%.6f rec.sum=%.6f KL.sum=%.6e (oracle rel err %.1e)" % (name, float(loss.sum()), float(rec.sum()), float(kl.sum()), err))
+    out = {"meta": np.array([B, nz, ns], dtype=np.int64), "kl_weight": np.float64(klw), "x": x.numpy(), "eps": eps.numpy(),
+           "loss": loss.numpy(), "rec": rec.numpy(), "kl": kl.numpy()}
+    for k, v in sd.items():
+        if "running_" in k or "num_batches" in k:
+            out["stat." + k] = v.numpy()
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref = load_reference_modules()
     out_dir = os.path.join(ROOT, "tests", "golden")
     run_case(ref, "omniglot_b8", 8, 32, 1, 0.1, out_dir)
     run_case(ref, "omniglot_b3_ns2", 3, 8, 2, 1.0, out_dir)
+    run_eval_case(ref, "omniglot_eval_b5", 5, 8, 1, 1.0, out_dir)
 
 
 if __name__ == "__main__":

@@ -226,3 +226,26 @@ def test_graphed_step_equals_eager_steps():
             assert_close(sd_b[k], sd_a[k], 1e-4, k, floor=1e-2)
         else:
             assert torch.equal(sd_a[k], sd_b[k]), k
+
+
+def test_image_eval_mode_vs_reference_golden(golden):
+    """eval() forward (running statistics; image.py test(), MI, sampling) on the fused tcgen05 path against the unmodified
+    reference's loss / rec / KL (fixture written by oracle/validate_image_against_reference.py::run_eval_case)."""
+    from modules.image import _ReparamKLFn
+    g = golden("omniglot_eval_b5")
+    B, nz, ns = [int(v) for v in g["meta"]]
+    vae, p = _build(nz)
+    sd = vae.state_dict()
+    for k in g:
+        if k.startswith("stat."):
+            sd[k[5:]] = torch.from_numpy(g[k]).cuda()
+    vae.load_state_dict(sd)
+    vae.eval()
+    x = torch.from_numpy(g["x"]).cuda()
+    with torch.no_grad():
+        mu, logvar = vae.encoder(x)
+        z, kl = _ReparamKLFn.apply(mu, logvar, torch.from_numpy(g["eps"]).cuda())
+        rec = vae.decoder.reconstruct_error(x, z).mean(dim=1)
+    assert_close(rec, g["rec"], 1e-4, "rec (eval)")
+    assert_close(kl, g["kl"], 1e-4, "kl (eval)", floor=1e-2)
+    assert_close(rec + float(g["kl_weight"]) * kl, g["loss"], 1e-4, "loss (eval)")

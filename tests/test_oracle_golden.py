@@ -147,3 +147,19 @@ def test_nll_iw_oracle_matches_reference(golden):
     with torch.no_grad():
         nll = O.nll_iw(p, x, [torch.from_numpy(e) for e in g2["eps"]])
     assert_close(nll, g2["nll"], 1e-6, "nll_iw")
+
+
+def test_image_oracle_eval_mode_vs_reference(golden):
+    """eval() forward of the image model (BatchNorm running statistics) of the oracle against the unmodified reference."""
+    import image_oracle as IO
+    g = golden("omniglot_eval_b5")
+    B, nz, ns = [int(v) for v in g["meta"]]
+    p = IO.init_image_params(nz, seed=0)
+    for k in g:
+        if k.startswith("stat."):
+            p[k[5:]] = torch.from_numpy(g[k])
+    with torch.no_grad():
+        loss, rec, kl = IO.vae_loss(p, torch.from_numpy(g["x"]), float(g["kl_weight"]), torch.from_numpy(g["eps"]), training=False)
+    assert_close(loss, g["loss"], 2e-5, "loss")
+    assert_close(rec, g["rec"], 2e-5, "rec")
+    assert_close(kl, g["kl"], 2e-5, "kl", floor=1e-2)
