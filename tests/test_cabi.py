@@ -118,3 +118,20 @@ def test_image_modules_refuse_cpu_tensors():
         vae.loss(torch.zeros(2, 1, 28, 28), 1.0)
     with pytest.raises(lagvae.LagvaeError):
         vae.decoder.decode(torch.zeros(2, 8), True)
+
+
+def test_bench_work_model_matches_survey_figures():
+    """The algorithmic-work figures bench.py / scripts/bench_sweep.py report against the numbers stated in SURVEY §8 d4
+    (Yahoo config: F_step = 1.2695 TFLOP, linear in B; compulsory HBM bytes ~1.4-1.5 GB at B=32)."""
+    import importlib.util
+    root = ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.CFG
+    F = bench.flops_step(c["B"], c["T"], c["V"], c["ni"], c["nh"], c["nz"])
+    assert abs(F - 1.2695e12) < 1e9
+    assert bench.flops_step(512, c["T"], c["V"], c["ni"], c["nh"], c["nz"]) == 16 * F
+    enc_fwd = 2 * 32 * (200 * 512 * 4096 + 200 * 1024 * 4096 + 1024 * 64)
+    assert abs(enc_fwd - 80.53e9) < 1e8                                  # encoder forward 80.53 GFLOP
+    assert bench.METRIC.startswith("aggressive inner-loop encoder steps/sec")
