@@ -365,3 +365,25 @@ def test_nll_iw_matches_reference(golden, monkeypatch):
         nll = vae.nll_iw(c["x"].cuda(), nsamples=len(g2["eps"]) * int(g2["ns"]), ns=int(g2["ns"]))
     assert not chunks
     assert_close(nll, g2["nll"], OUT_TOL, "nll_iw")
+
+
+def test_fused_inner_step_full_shape_loss_and_norm(golden):
+    """Fused inner step at the Yahoo shape (the only shape where the norm-only dW_pred GEMM runs on the side stream under
+    the decoder recurrence): Σloss and the clip norm of all 13 gradients against the unmodified reference's values."""
+    g = golden("yahoo_eval")
+    V, ni, nh, nz, B, T, ns, _ = [int(v) for v in g["meta"]]
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=0), 4.0)
+    import lagvae
+    eng = lagvae.TextEngine(V, ni, nh, nz, "cuda")
+    x = O.make_token_batch(B, T, V).cuda()
+    eps = torch.from_numpy(g["eps"]).cuda()
+    gw = eng.grad_workspace()
+    out_loss, sc = torch.empty(B, device="cuda"), torch.empty(4, device="cuda")
+    for rep in range(2):                       # twice: the staging arena and the side stream are reused across steps
+        params = _plist(p)
+        eng.inner_step(params, x, eps, float(g["kl_weight"]), None, gw, out_loss, sc)
+        assert_close(out_loss, g["loss"], OUT_TOL, "loss")
+        assert abs(float(sc[3]) - float(g["grad_norm"])) <= 1e-3 * float(g["grad_norm"]), (rep, float(sc[3]), float(g["grad_norm"]))
+    grads = eng.split_grads(gw)
+    n_pred = float(grads[12].double().norm())
+    assert abs(n_pred - float(g["gnorm.decoder.pred_linear.weight"])) <= 2e-3 * float(g["gnorm.decoder.pred_linear.weight"])

@@ -344,6 +344,11 @@ int num_sms() {
 
 }  // namespace
 
+// Optional cap on the persistent grid of the NEXT gemm_tc launches of this thread (0 = one CTA per SM): lets a GEMM run on
+// the SMs a co-resident persistent kernel leaves idle (text_plan.cu: weight-gradient GEMM under the LSTM recurrence).
+static thread_local int tl_grid_cap = 0;
+void gemm_tc_set_grid_cap(int max_ctas) { tl_grid_cap = max_ctas > 0 ? max_ctas : 0; }
+
 int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M, int N, int K, int passes,
             float alpha, float beta, const float* bias_n, const float* bias_rows, int bias_period,
             const int32_t* out_row_map, cudaStream_t st) {
@@ -371,7 +376,7 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M
   }
   GemmArgs g{C, ldc, M, N, K, passes, alpha, beta, bias_n, bias_rows, bias_period, out_row_map};
   const int tiles = (int)(cdiv(M, BM) * cdiv(N, BN));
-  const int grid = std::min(tiles, num_sms());
+  const int grid = std::min(tiles, tl_grid_cap ? std::min(tl_grid_cap, num_sms()) : num_sms());
   const int key = (A.mn_major ? 2 : 0) | (B.mn_major ? 1 : 0);
   if (BN == 256) {
     switch (key) {

@@ -143,6 +143,7 @@ struct TcOperand {
 int gemm_tc(const TcOperand& A, const TcOperand& B, float* C, int64_t ldc, int M, int N, int K,
             int passes, float alpha, float beta, const float* bias_n, const float* bias_rows,
             int bias_period, const int32_t* out_row_map, cudaStream_t st);
+void gemm_tc_set_grid_cap(int max_ctas);   // 0 = default (one CTA per SM); applies to this thread's next launches
 int split_bf16_launch(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, cudaStream_t st);
 

@@ -45,6 +45,12 @@ struct lagvae_text_plan {
   LstmTcState* lstm_tc;  // persistent tcgen05 LSTM state (nullptr when unsupported / SIMT)
   cudaEvent_t dec_ev;    // optional: recorded when the decoder gradients are final (data-parallel overlap hook)
   bool dec_ev_recorded;
+  // side stream for the norm-only dW_pred GEMM: it runs on the 20 SMs the 128-CTA persistent decoder recurrence leaves
+  // idle (scripts/microbench/overlap_probe.py: both launch orders overlap fully) and is joined before the decoder
+  // gradients are declared final
+  cudaStream_t side;
+  cudaEvent_t side_fork, side_join;
+  size_t arena_floor;    // staging below this offset is still read by the side stream
   // state carried from forward to backward
   lagvae_dropout drop;
   float kl_weight;
@@ -416,6 +422,9 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
   P->base = (char*)workspace;
   carve(P, P->base);
   P->lstm_tc = nullptr;
+  P->side = nullptr;
+  P->side_fork = P->side_join = nullptr;
+  P->arena_floor = 0;
   // LAGVAE_NO_LSTM_TC=1 keeps the tensor-core GEMMs but runs the recurrence on the launch-per-step tier
   const char* no_rec = getenv("LAGVAE_NO_LSTM_TC");
   const bool rec_tc = P->use_tc && !(no_rec && no_rec[0] == '1');
@@ -434,6 +443,9 @@ void lagvae_text_plan_destroy(lagvae_text_plan* P) {
   if (!P) return;
   lstm_tc_destroy(P->lstm_tc);
   if (P->dec_ev) cudaEventDestroy(P->dec_ev);
+  if (P->side_fork) cudaEventDestroy(P->side_fork);
+  if (P->side_join) cudaEventDestroy(P->side_join);
+  if (P->side) cudaStreamDestroy(P->side);
   delete P;
 }
 
@@ -534,7 +546,12 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   const DropSpec din = spec_in(P->drop), dout = spec_out(P->drop);
   int status = LAGVAE_OK;
   P->arena_off = 0;
+  P->arena_floor = 0;
   P->have_forward = false;  // logits are consumed in place
+  // norm-only dW_pred on a side stream under the decoder recurrence (LAGVAE_SIDE_WGRAD=0 disables)
+  static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return !(e && e[0] == '0'); }();
+  const bool side_wgrad = side_env && P->use_tc && P->lstm_tc && P->dec_wgrad_passes == 1 && nh == 1024 && Bd <= 256;
+  bool side_pending = false;
 
   LV_TRY(combine_upstream(g_loss, g_rec, g_kl, P->kl_weight, B, P->g_rec, P->g_kl, st));
 
@@ -559,10 +576,28 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     // dH_drop [rd, nh] = dlogits · W_pred
     LV_TRY(mm(P, sdl, false, swp, true, P->dh_d, nh, (int)rd, nh, V, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
     // dW_pred [V, nh] = dlogitsᵀ · H_drop
-    LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
-              P->dec_wgrad_passes, st));
+    if (side_wgrad && tc_dl && sdl.tc.hi && sh.tc.hi) {
+      if (!P->side) {
+        LV_CUDA(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+        LV_CUDA(cudaEventCreateWithFlags(&P->side_fork, cudaEventDisableTiming));
+        LV_CUDA(cudaEventCreateWithFlags(&P->side_join, cudaEventDisableTiming));
+      }
+      LV_CUDA(cudaEventRecord(P->side_fork, st));          // operands staged, dH GEMM enqueued ahead of the recurrence
+      LV_CUDA(cudaStreamWaitEvent(P->side, P->side_fork, 0));
+      gemm_tc_set_grid_cap(20);                            // 148 SMs - 128 recurrence CTAs
+      const int rs = mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
+                        P->dec_wgrad_passes, P->side);
+      gemm_tc_set_grid_cap(0);
+      LV_TRY(rs);
+      LV_CUDA(cudaEventRecord(P->side_join, P->side));
+      side_pending = true;
+      P->arena_floor = P->arena_off;                       // dlogits / H_drop staging stays live until the join
+    } else {
+      LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
+                P->dec_wgrad_passes, st));
+    }
   }
-  P->arena_off = 0;  // dlogits staging no longer needed
+  P->arena_off = P->arena_floor;  // dlogits staging no longer needed (unless the side stream still reads it)
 
   // ---- decoder LSTM backward (cuDNN RNN backward in the reference)
   if (P->lstm_tc)
@@ -603,6 +638,11 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
                   nullptr, 0, st));
   LV_TRY(gemm_f32(P->dc0t, nh, 1, w->p[D_TRANS], 1, nz, P->dz, nz, Bd, nz, nh, 1.f, 1.f, nullptr, nullptr, 0, st));
 
+  if (side_pending) {   // dW_pred finished long ago (≈1.1 ms on 20 SMs vs 1.7 ms of recurrence): join, free its staging
+    LV_CUDA(cudaStreamWaitEvent(st, P->side_join, 0));
+    side_pending = false;
+    P->arena_floor = 0;
+  }
   // all 7 decoder gradients are final here: data-parallel callers may start reducing them (lagvae.h)
   if (P->dec_ev) {
     LV_CUDA(cudaEventRecord(P->dec_ev, st));
