@@ -548,8 +548,10 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   P->arena_off = 0;
   P->arena_floor = 0;
   P->have_forward = false;  // logits are consumed in place
-  // norm-only dW_pred on a side stream under the decoder recurrence (LAGVAE_SIDE_WGRAD=0 disables)
-  static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return !(e && e[0] == '0'); }();
+  // norm-only dW_pred on a side stream under the decoder recurrence: OPT-IN (LAGVAE_SIDE_WGRAD=1).  Correct (the
+  // full-shape fused-step test passes with it), but measured SLOWER on the B200: 10.22 vs 9.49 ms/step — the 20 GEMM CTAs
+  // delay the co-residency of the backward recurrence's clusters of 4 (profiles/README.md, r1i); kept for the next round.
+  static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return e && e[0] == '1'; }();
   const bool side_wgrad = side_env && P->use_tc && P->lstm_tc && P->dec_wgrad_passes == 1 && nh == 1024 && Bd <= 256;
   bool side_pending = false;
 
