@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Probe for DESIGN §9 item 3: does a 20-CTA tcgen05 GEMM on a side stream run CONCURRENTLY with the persistent
-128-CTA cooperative-cluster LSTM recurrence (which leaves 20 of the 148 SMs idle)?  Times the LSTM forward alone, the
-GEMM alone, and both (LSTM launched first / GEMM launched first) with CUDA events; overlap works when
-t(both) ~= max(t_lstm, t_gemm) instead of the sum."""
+128-CTA cooperative-cluster LSTM recurrence (which leaves 20 of the 148 SMs idle)?  Times the LSTM forward (clusters of
+2) and backward (clusters of 4) alone, the GEMM alone, and both (LSTM launched first / GEMM launched first) with CUDA
+events; overlap works when t(both) ~= max(t_lstm, t_gemm) instead of the sum.  r1i: forward overlaps fully in both
+orders; the backward case is the open question behind the slower LAGVAE_SIDE_WGRAD=1 step (profiles/README.md)."""
 import ctypes as C
 import os
 import sys
@@ -34,15 +35,25 @@ def lstm(stream):
                                    C.byref(drop), be.ptr(ws), ws.numel(), C.c_void_p(stream.cuda_stream)))
 
 
+dh = torch.randn(Tn * Bd, nh, device=dev) * 0.01
+dc, dhr, dg = torch.zeros(Bd, nh, device=dev), torch.zeros(Bd, nh, device=dev), torch.zeros(Tn * Bd, 4 * nh, device=dev)
+
+
+def lstm_bwd(stream):
+    be.check(L.lagvae_lstm_backward(1, nh, Tn, Bd, be.ptr(w_hh), None, be.ptr(gates), be.ptr(c_all), be.ptr(dh), None, C.byref(drop),
+                                    be.ptr(dc), be.ptr(dhr), be.ptr(dg), 1, be.ptr(ws), ws.numel(), C.c_void_p(stream.cuda_stream)))
+
+
 def gemm(stream):
     be.check(L.lagvae_gemm_tc(be.ptr(A), be.ptr(A), K, 0, be.ptr(Bm), be.ptr(Bm), K, 0, be.ptr(out), N, M, N, K, 1, 1.0, 0.0,
                               None, None, 0, None, C.c_void_p(stream.cuda_stream)))
 
 
-def timed(fn, reps=5):
+def timed(fn, reps=5, restore=True):
     ts = []
     for _ in range(reps):
-        gates.copy_(pre)
+        if restore:
+            gates.copy_(pre)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()                       # default stream; both work streams wait on it
@@ -69,3 +80,15 @@ t_lg = timed(lambda: (lstm(s_main), gemm(s_side)))
 t_gl = timed(lambda: (gemm(s_side), lstm(s_main)))
 print("lstm alone %.3f ms | 20-CTA gemm alone %.3f ms | lstm then gemm %.3f ms | gemm then lstm %.3f ms | sum %.3f max %.3f"
       % (t_l, t_g, t_lg, t_gl, t_l + t_g, max(t_l, t_g)))
+
+# backward recurrence (clusters of 4) on the activated gates the forward left behind
+gates.copy_(pre)
+lstm(s_main)
+torch.cuda.synchronize()
+lstm_bwd(s_main)
+torch.cuda.synchronize()
+t_b = timed(lambda: lstm_bwd(s_main), restore=False)
+t_bg = timed(lambda: (lstm_bwd(s_main), gemm(s_side)), restore=False)
+t_gb = timed(lambda: (gemm(s_side), lstm_bwd(s_main)), restore=False)
+print("lstm BWD alone %.3f ms | 20-CTA gemm alone %.3f ms | bwd then gemm %.3f ms | gemm then bwd %.3f ms | sum %.3f max %.3f"
+      % (t_b, t_g, t_bg, t_gb, t_b + t_g, max(t_b, t_g)))
