@@ -205,6 +205,12 @@ int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, co
  * accumulators complete, epilogue stores issued).  NULL disables (default). */
 void lagvae_debug_trace_buffer(void* dev_u64, size_t words);
 
+/* Which recurrence kernel the most recent LSTM forward (direction 0) / backward (direction 1) launch of this process
+ * used: "v2/cs<N>" (persistent cluster kernel, cluster size N), "v1" (persistent, no cluster), "steps" (launch per
+ * time step, fp32 SIMT) or "none".  A variant that was selected and then fails to launch is an error, never a silent
+ * fallback; tests and bench.py assert the variant they mean to measure (nn.LSTM at enc_lstm.py:60, dec_lstm.py:104). */
+const char* lagvae_lstm_variant(int direction);
+
 /* fp32 [rows, cols] (ld) -> bf16 hi/lo [rows, ld_out] (zero padded columns cols..ld_out). */
 int lagvae_split_bf16(const float* src, int64_t ld, int rows, int cols, uint16_t* hi, uint16_t* lo,
                       int64_t ld_out, void* stream);

@@ -232,32 +232,41 @@ def run_generation_case(ref, name, V, ni, nh, nz, n, out_dir):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--yahoo", action="store_true", help="also run the Yahoo-shape KAT (slow)")
+    ap.add_argument("--yahoo-train", dest="yahoo_train", action="store_true", help="only the Yahoo-shape train()-mode fixture")
+    ap.add_argument("--only-big", action="store_true", help="skip the small cases")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     ref = load_reference_modules()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    # config #1 of BASELINE.json (toy.py: nz=1, toy.py:102), eval + train-mode masks
-    run_case(ref, "toy_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.5, out_dir)
-    run_case(ref, "toy_train", 1004, 50, 50, 1, 32, 12, 1, True, 0.5, 1.5, out_dir)
-    # ragged batch (< batch_size rows, text_data.py:241-247) + odd sizes
-    run_case(ref, "ragged_train", 301, 24, 40, 3, 5, 7, 1, True, 0.1, 1.5, out_dir)
-    # tensor-core-aligned small shape
-    run_case(ref, "aligned_train", 520, 64, 128, 8, 16, 10, 1, True, 0.1, 1.5, out_dir)
-    # multi-sample forward (nsamples>1: dec_lstm.py:86-94,139-140)
-    run_case(ref, "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 3, False, 1.0, 1.5, out_dir)
-    # KL ~ 0 regime at the stock init (no head scaling) — conditioning check
-    run_case(ref, "toy_stockinit_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.0, out_dir)
-    run_generation_case(ref, "generation_small", 24, 16, 32, 4, 8, out_dir)
-    run_nll_iw_case(ref, "aligned_nll_iw", "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 6, 3, out_dir)
+    if not a.only_big:
+        # config #1 of BASELINE.json (toy.py: nz=1, toy.py:102), eval + train-mode masks
+        run_case(ref, "toy_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.5, out_dir)
+        run_case(ref, "toy_train", 1004, 50, 50, 1, 32, 12, 1, True, 0.5, 1.5, out_dir)
+        # ragged batch (< batch_size rows, text_data.py:241-247) + odd sizes
+        run_case(ref, "ragged_train", 301, 24, 40, 3, 5, 7, 1, True, 0.1, 1.5, out_dir)
+        # tensor-core-aligned small shape
+        run_case(ref, "aligned_train", 520, 64, 128, 8, 16, 10, 1, True, 0.1, 1.5, out_dir)
+        # multi-sample forward (nsamples>1: dec_lstm.py:86-94,139-140)
+        run_case(ref, "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 3, False, 1.0, 1.5, out_dir)
+        # KL ~ 0 regime at the stock init (no head scaling) — conditioning check
+        run_case(ref, "toy_stockinit_eval", 1004, 50, 50, 1, 32, 12, 1, False, 1.0, 1.0, out_dir)
+        run_generation_case(ref, "generation_small", 24, 16, 32, 4, 8, out_dir)
+        run_nll_iw_case(ref, "aligned_nll_iw", "aligned_ns3_eval", 520, 64, 128, 8, 8, 9, 6, 3, out_dir)
     if a.yahoo:
         # BASELINE.json configs[1] and configs[2] at their full shapes; the parameters are regenerated in the tests from
         # O.init_text_params(seed) (the reference is built FROM the oracle parameters here), fixtures keep fingerprints
         run_big_case(ref, "yahoo_eval", 20001, 512, 1024, 32, 32, 200, 0.1, out_dir)
         run_big_case(ref, "yelp_eval", 19997, 512, 1024, 32, 32, 100, 1.0, out_dir)
+    if a.yahoo or a.yahoo_train:
+        # the configuration bench.py times: Yahoo shape, train() mode (dropout 0.5/0.5), kl_weight 0.1
+        run_big_case(ref, "yahoo_train", 20001, 512, 1024, 32, 32, 200, 0.1, out_dir, train=True)
 
 
-def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir):
+def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir, train=False):
+    """Full-shape fingerprint fixture.  train=True: train() mode with the reference's own dropout draws (replayed and
+    stored bit-packed: np.packbits over the flattened keep-masks, ~1.2 MB at the Yahoo shape) — the configuration
+    bench.py times; also stores the post-step encoder parameters (clip 5.0 + SGD lr 1, text.py:385-387) as fingerprints."""
     vae = build_reference(ref, V, ni, nh, nz, 0.5, 0.5)
     p0 = O.init_text_params(V, ni, nh, nz, seed=0)
     O.scale_trained_like(p0, 4.0)
@@ -265,7 +274,7 @@ def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir):
     sd.update(p0)
     vae.load_state_dict(sd)
     x = O.make_token_batch(B, T, V)
-    vae.eval()
+    vae.train() if train else vae.eval()
     torch.manual_seed(1)
     loss, rec, kl = vae.loss(x, klw)
     vae.zero_grad()
@@ -274,14 +283,32 @@ def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir):
     gn = float(torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0))
     torch.manual_seed(1)
     eps = torch.zeros(B, 1, nz).normal_()
+    out = {}
+    if train:
+        mask_in = torch.nn.functional.dropout(torch.ones(B, T - 1, ni), 0.5, True) != 0                      # dec_lstm.py:81
+        mask_out = torch.nn.functional.dropout(torch.ones(T - 1, B, nh).transpose(0, 1), 0.5, True) != 0    # dec_lstm.py:106
+        # the replayed draws must be the ones the reference consumed: check through the oracle's loss
+        o_loss, _, _ = O.vae_loss({k: v.clone() for k, v in p0.items()}, x, klw, eps, mask_in.float() * 2, mask_out.float() * 2)
+        err = float((o_loss - loss.detach()).abs().max() / loss.detach().abs().max())
+        assert err < 2e-5, (name, "replayed dropout masks do not reproduce the reference loss", err)
+        out["mask_in_bits"] = np.packbits(mask_in.contiguous().numpy().reshape(-1))
+        out["mask_out_bits"] = np.packbits(mask_out.contiguous().numpy().reshape(-1))
+        torch.optim.SGD(vae.encoder.parameters(), lr=1.0, momentum=0).step()                 # text.py:387
+        for k, q in zip(O.ENC_KEYS, vae.encoder.parameters()):
+            q = q.detach()
+            out["postnorm." + k] = np.float64(q.double().norm())
+            out["postslice." + k] = q.reshape(-1)[:: max(1, q.numel() // 64)][:64].numpy()
+            out["dnorm." + k] = np.float64((q - p0[k]).double().norm())     # size of the update itself
+        vae.load_state_dict({**vae.state_dict(), **p0})
+    vae.eval()
     torch.manual_seed(2)
     mi = vae.calc_mi_q(x)
     torch.manual_seed(2)
     eps_mi = torch.zeros(B, 1, nz).normal_()
-    out = {"meta": np.array([V, ni, nh, nz, B, T, 1, 0], dtype=np.int64), "kl_weight": np.float64(klw),
-           "eps": eps.numpy(), "eps_mi": eps_mi.numpy(), "loss": loss.detach().numpy(),
-           "rec": rec.detach().numpy(), "kl": kl.detach().numpy(), "mi": np.float64(mi),
-           "grad_norm": np.float64(gn)}
+    out.update({"meta": np.array([V, ni, nh, nz, B, T, 1, int(train)], dtype=np.int64), "kl_weight": np.float64(klw),
+                "eps": eps.numpy(), "eps_mi": eps_mi.numpy(), "loss": loss.detach().numpy(),
+                "rec": rec.detach().numpy(), "kl": kl.detach().numpy(), "mi": np.float64(mi),
+                "grad_norm": np.float64(gn)})
     mu, lv = vae.encode_stats(x)
     out["mu"], out["logvar"] = mu.detach().numpy(), lv.detach().numpy()
     for k in O.ALL_KEYS:

@@ -68,7 +68,8 @@ def _worker(rank, world, port, B, out_q, two_buckets=False):
     lo, hi = shard_bounds(B, rank, world)
     dec_off = sum(q.numel() for q in params[:6]) if two_buckets else None
     loss_sum, norm = dp_inner_step(OracleBackend(eps, 0.5, lo, dec_off), params, x, flat, max_norm=0.05)
-    out_q.put((rank, loss_sum, norm, [q.clone() for q in params[:6]]))
+    out_q.put((rank, loss_sum, norm, [q.numpy().copy() for q in params[:6]]))   # numpy: pickled by value (a torch tensor
+    # travels as a shared-memory fd that dies with this process)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,6 +86,7 @@ def test_two_rank_gloo_equals_single_process(B, two_buckets):
     for pr in procs:
         pr.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    res = [(a, b, c, [torch.from_numpy(e) for e in d]) for a, b, c, d in res]
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0

@@ -18,6 +18,7 @@
 #include "lstm_tc.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 
@@ -985,6 +986,12 @@ struct LstmTcState {
 
 constexpr int64_t MISC_BYTES = 1024 /*align slack*/ + 8 * (2 * MAX_NS + MAX_MT + 1) + 64;
 
+// which recurrence kernel the last forward / backward launch used ("v2/cs2", "v1", "steps", ...): exported through
+// lagvae_lstm_variant so that tests and bench.py can assert that the intended kernel ran (no silent fallback)
+static char g_variant[2][32] = {"none", "none"};
+void lstm_note_variant(int dir, const char* what) { snprintf(g_variant[dir & 1], sizeof(g_variant[0]), "%s", what); }
+const char* lstm_last_variant(int dir) { return g_variant[dir & 1]; }
+
 static unsigned long long* g_dbg = nullptr;   // optional device trace buffer (lagvae_debug_trace_buffer)
 static size_t g_dbg_words = 0;
 void lstm_tc_set_debug(void* p, size_t words) {
@@ -1094,17 +1101,17 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
 template <bool FWD, int CS_>
 static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, size_t smem, cudaStream_t st, bool* launched) {
   using C = V2Cfg<FWD, CS_>;
-  static int state = 0;   // 0 unknown, 1 cooperative+cluster ok, 2 cluster only, -1 unavailable
+  // per-device decision, made ONCE from an occupancy query (no trial launches): 1 = all clusters of this size are
+  // co-resident (the per-step grid barrier needs that), -1 = they are not (the caller picks another cluster size).
+  // After a positive decision a failing launch is an ERROR: nothing falls back silently (lagvae_lstm_variant reports
+  // what ran).  The kernel spins on a grid-wide counter, so the launch is always cooperative.
+  static int state[16] = {0};
+  int dev = 0;
+  LV_CUDA(cudaGetDevice(&dev));
+  int& stt = state[dev & 15];
   *launched = false;
-  if (state < 0) return LAGVAE_OK;
+  if (stt < 0) return LAGVAE_OK;
   auto kern = k_lstm_v2<FWD, CS_>;
-  if (state == 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
-      cudaGetLastError();
-      state = -1;
-      return LAGVAE_OK;
-    }
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(s->G);
   cfg.blockDim = dim3(NTHREADS);
@@ -1118,43 +1125,33 @@ static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, si
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  if (state == 0) {   // all clusters must be co-resident for the grid barrier
+  if (stt == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+      cudaGetLastError();
+      stt = -1;
+      return LAGVAE_OK;
+    }
     int ncl = 0;
     cfg.numAttrs = 1;
     if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl * C::CS < s->G) {
       cudaGetLastError();
-      state = -1;
+      stt = -1;
       return LAGVAE_OK;
     }
+    stt = 1;
   }
-  if (state == 0 || state == 1) {
-    cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tm);
-    if (e == cudaSuccess) {
-      state = 1;
-      *launched = true;
-      g_launches.fetch_add(1);
-      return LAGVAE_OK;
-    }
-    cudaGetLastError();
-    if (state == 1) {
-      set_error("lstm v2 launch failed: %s", cudaGetErrorString(e));
-      return LAGVAE_E_CUDA;
-    }
-  }
-  cfg.numAttrs = 1;   // cluster launch without the cooperative attribute (grid fits: checked above)
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tm);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    if (state == 2) {
-      set_error("lstm v2 launch failed: %s", cudaGetErrorString(e));
-      return LAGVAE_E_CUDA;
-    }
-    state = -1;
-    return LAGVAE_OK;
+    set_error("lstm v2 (%s, cluster of %d) cooperative launch failed: %s", FWD ? "forward" : "backward", C::CS,
+              cudaGetErrorString(e));
+    return LAGVAE_E_CUDA;
   }
-  state = 2;
   *launched = true;
+  char nm[32];
+  snprintf(nm, sizeof(nm), "v2/cs%d", C::CS);
+  lstm_note_variant(FWD ? 0 : 1, nm);
   g_launches.fetch_add(1);
   return LAGVAE_OK;
 }
@@ -1217,6 +1214,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   }
   void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
+  lstm_note_variant(0, "v1");
   g_launches.fetch_add(1);
   return LAGVAE_OK;
 }
@@ -1229,7 +1227,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   RecArgs a{};
   a.nh = s->nh; a.Bd = Bd; a.Tn = Tn;
   size_t smem = 0;
-  static int cs_ok = 8;   // 16 clusters of 8 CTAs do not fit on every B200 (GPC sizes): fall back to clusters of 4
+  static int cs_ok = 8;   // (process-wide; one device model per process) 16 clusters of 8 CTAs do not fit on every B200 (GPC sizes): fall back to clusters of 4
   bool v2 = cs_ok == 8 && v2_geometry<false, 8>(s, Bd, &a, &smem);
   int v2cs = v2 ? 8 : 0;
   if (!v2 && cs_ok >= 4) {
@@ -1272,6 +1270,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   }
   void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_bwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
+  lstm_note_variant(1, "v1");
   g_launches.fetch_add(1);
   return LAGVAE_OK;
 }

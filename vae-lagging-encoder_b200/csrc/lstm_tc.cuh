@@ -10,6 +10,8 @@ size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc);
 // returns LAGVAE_OK with *out == nullptr when the shape is not covered by the persistent kernels
 int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_bytes, LstmTcState** out);
 void lstm_tc_destroy(LstmTcState* s);
+void lstm_note_variant(int dir, const char* what);      // dir 0 = forward, 1 = backward
+const char* lstm_last_variant(int dir);
 void lstm_tc_set_debug(void* dev_u64, size_t words);   // optional clock64 trace buffer of CTA 0 ([step][8])
 // Same contracts as lstm_forward_steps / lstm_backward_steps in text_plan.cu.
 int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,

@@ -259,6 +259,7 @@ int lstm_forward_steps(const float* w_hh, const float* h0, const float* c0, floa
                        float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd, int nh,
                        cudaStream_t st) {
   const int64_t gs = (int64_t)Bd * 4 * nh, hs = (int64_t)Bd * nh;
+  lstm_note_variant(0, "steps");
   for (int t = 0; t < Tn; ++t) {
     const float* hp = t ? h_all + (t - 1) * hs : h0;
     const float* cp = t ? c_all + (t - 1) * hs : c0;
@@ -279,6 +280,7 @@ int lstm_backward_steps(const float* w_hh, const float* c0, const float* gates, 
                         cudaStream_t st) {
   const int64_t gs = (int64_t)Bd * 4 * nh, hs = (int64_t)Bd * nh;
   LV_TRY(fill(dc, 0.f, hs, st));
+  lstm_note_variant(1, "steps");
   for (int t = Tn - 1; t >= 0; --t) {
     // dh_last (gradient on the final h only) adds to dh_ext at t = Tn-1; it rides in the dh_rec slot there
     const float* ext = dh_ext ? dh_ext + t * hs : (t == Tn - 1 ? dh_last : nullptr);
@@ -794,6 +796,8 @@ int lagvae_lstm_backward(int tier, int nh, int Tn, int Bd, const float* w_hh, co
 }
 
 void lagvae_debug_trace_buffer(void* dev_u64, size_t words) { lstm_tc_set_debug(dev_u64, words); }
+
+const char* lagvae_lstm_variant(int direction) { return lstm_last_variant(direction); }
 
 int lagvae_gemm_f32(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
                     float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, const float* bias_n,

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "lagvae_lstm_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _vp, _i,
                                   _vp, _sz, _vp]),
     "lagvae_debug_trace_buffer": (None, [_vp, _sz]),
+    "lagvae_lstm_variant": (C.c_char_p, [_i]),
     "lagvae_im2col": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lagvae_col2im": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lagvae_bn_train_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -150,3 +151,9 @@ def ptr(t):
 
 def launch_count():
     return int(lib().lagvae_launch_count())
+
+
+def lstm_variant():
+    """{'forward': ..., 'backward': ...}: the recurrence kernels the most recent LSTM launches used (lagvae.h)."""
+    L = lib()
+    return {"forward": L.lagvae_lstm_variant(0).decode(), "backward": L.lagvae_lstm_variant(1).decode()}
