@@ -9,8 +9,8 @@ backward of mean(loss), clip_grad_norm_(all 13 tensors, 5.0), SGD step on the 6 
 ours:       `value`  fused lagvae_text_inner_step, inputs resident in HBM, CUDA events, max over ranks
             `e2e`    the drop-in `modules.VAE` API exactly as text.py:373-387 drives it, token ids in PINNED
                      HOST memory copied H2D every step, Σloss read back D2H every step
-reference:  the CPU port of the reference path (oracle.FastPort: the reference's own torch layer types) on
-            all host cores, each step a bounded sample (B_s of the 32 sentences), rate scaled to full steps.
+reference:  the reference's own modules (a staged copy: $VAE_REF_PATH / baseline/_ref; else oracle.FastPort, the same
+            torch layer types) on the host cores, FULL 32-sentence steps, the sample bounded in the number of steps.
 N > 1:      one process per GPU (torchrun), batch-sharded data parallel: every rank runs the same step on
             its own 32-sentence shard, ONE NCCL all-reduce of the flat 53.8 M-float gradient per step, then
             clip + SGD on the averaged gradient.  Weak scaling: global batch = 32 N.
@@ -86,95 +86,121 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------
-def _calibrate_cpu_port(budget_s=40.0):
-    """Pick the host thread count at which the CPU port actually runs fastest on this box.  oneDNN's LSTM
-    with a handful of sentences per step and 200 dependent time steps scales NEGATIVELY beyond a few dozen
-    threads (measured: 128 threads were 30x slower than 8 on the B200 host), so "all the host threads it can
-    use" is found by trying 8, 16, 32, ... up to every core on a ONE-sentence step and keeping the best.
-    Returns (model, threads, seconds per one-sentence step)."""
+def _reference_stepper(device):
+    """The reference's OWN modules ($VAE_REF_PATH -> baseline/_ref -> /root/reference) driven by the statement sequence
+    of text.py:373-387; the oracle's port (the same torch layer types, oracle.FastPort) only when no copy of the reference
+    is present.  Returns (stepper, kind) with kind "reference" | "port"."""
+    import lagging_oracle as O
+    import reference_loader as R
+    c = CFG
+    ref = R.load_reference_modules()
+    if ref is not None:
+        vae = R.build_reference_vae(ref, c["V"], c["ni"], c["nh"], c["nz"], device)
+        return R.ReferenceStepper(vae), "reference"
+    torch.manual_seed(0)
+    return O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).to(device).train(), "port"
+
+
+def _host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def _calibrate_threads(m, budget_s=30.0):
+    """oneDNN's LSTM with 200 dependent time steps can scale NEGATIVELY with the thread count on many-core hosts
+    (measured in round 1: 128 threads 30x slower than 8), so "all the host threads it can use" is found by timing an
+    8-sentence step at every core and at a few smaller counts and keeping the fastest.  Full-batch steps are then timed
+    at that count; nothing is extrapolated."""
     import lagging_oracle as O
     c = CFG
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    torch.manual_seed(0)
-    m = O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).train()
-    x1 = O.make_token_batch(1, c["T"], c["V"], seed=77)
-    cands = sorted({min(ncpu, t) for t in (8, 16, 32, 64, ncpu)})
-    best_t, best_th, t_start = None, cands[0], time.perf_counter()
+    ncpu = _host_threads()
+    x8 = O.make_token_batch(8, c["T"], c["V"], seed=77)
+    cands = sorted({min(ncpu, t) for t in (ncpu, ncpu // 2, 32, 16)} - {0}, reverse=True)
+    best_t, best_th, t_start = None, ncpu, time.perf_counter()
     for th in cands:
         torch.set_num_threads(th)
-        m.inner_step(x1, KL_WEIGHT)                   # warm (allocator, oneDNN primitive cache)
+        m.inner_step(x8, KL_WEIGHT)                   # warm (allocator, oneDNN primitive cache)
         t0 = time.perf_counter()
-        m.inner_step(x1, KL_WEIGHT)
+        m.inner_step(x8, KL_WEIGHT)
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best_t, best_th = dt, th
-        if dt > 1.5 * best_t or time.perf_counter() - t_start > budget_s:
+        if time.perf_counter() - t_start > budget_s:
             break
     torch.set_num_threads(best_th)
-    return m, best_th, best_t, ncpu
+    return best_th, ncpu
 
 
-def _cpu_port_rate(n_steps, n_warm, budget_s):
-    """Time the CPU port on a bounded sample: each step = Bs of the 32 sentences at full T=200 (every layer of the
-    path at its real K/N sizes; only the batch rows are sampled), Bs chosen so the whole run fits `budget_s`."""
+def _cpu_reference_rate(n_steps, n_warm, budget_s):
+    """Time FULL 32-sentence steps of the reference path on the host cores.  The sample is bounded in the number of steps
+    (as many of the requested K as fit `budget_s`, at least 2), never in the batch: a full step is the unit of the metric."""
     import lagging_oracle as O
     c = CFG
-    m, th, t1, ncpu = _calibrate_cpu_port()
-    Bs = int(max(1, min(c["B"], budget_s / max(1e-3, (n_steps + n_warm) * t1))))
-    Bs = 1 << (Bs.bit_length() - 1)                    # 1, 2, 4, ... 32
-    xs = [O.make_token_batch(Bs, c["T"], c["V"], seed=1234 + i) for i in range(4)]
-    for i in range(n_warm):
-        m.inner_step(xs[i % 4], KL_WEIGHT)
+    m, kind = _reference_stepper("cpu")
+    th, ncpu = _calibrate_threads(m)
+    xs = [O.make_token_batch(c["B"], c["T"], c["V"], seed=1234 + i) for i in range(4)]
     t0 = time.perf_counter()
-    for i in range(n_steps):
+    m.inner_step(xs[0], KL_WEIGHT)                   # warm-up step, also the estimate of a step's cost
+    t1 = time.perf_counter() - t0
+    n_w = max(0, min(n_warm, 3) - 1)
+    n_t = int(max(2, min(n_steps, (budget_s - t1 * (1 + n_w)) / max(t1, 1e-3))))
+    for i in range(n_w):
+        m.inner_step(xs[(1 + i) % 4], KL_WEIGHT)
+    t0 = time.perf_counter()
+    for i in range(n_t):
         m.inner_step(xs[i % 4], KL_WEIGHT)
     dt = time.perf_counter() - t0
-    rate = n_steps / dt * (Bs / c["B"])               # full 32-sentence steps per second
-    sample = ("%d timed steps of %d/%d sentences x T=%d (oracle.FastPort = the reference's torch layer types on CPU), rate scaled "
-              "by %d/%d; %d of %d host threads (fastest of the calibrated thread counts)" % (n_steps, Bs, c["B"], c["T"], Bs, c["B"], th, ncpu))
-    return rate, th, sample
+    rate = n_t / dt
+    what = "the reference's own modules (VAE.loss -> backward -> clip_grad_norm_ -> SGD.step, text.py:373-387)" if kind == "reference" \
+        else "oracle.FastPort (the reference's torch layer types; no copy of the reference on this box)"
+    sample = ("%d timed full steps (32 sentences x T=%d, train mode) after %d warm-up steps of %s on the host CPU; "
+              "%d of %d host threads (fastest of the calibrated counts); no extrapolation" % (n_t, c["T"], 1 + n_w, what, th, ncpu))
+    return rate, th, kind, sample
 
 
 def run_reference(args, rank, world):
-    """Reference arm: CPU port on the host cores (rank 0 only), bounded to a couple of minutes whatever K and W."""
+    """Reference arm: the reference path on the host cores (rank 0 only), bounded to a few minutes whatever K and W."""
     if rank != 0:
         return
-    rate, th, sample = _cpu_port_rate(args.steps, args.warmup, budget_s=100.0)
+    rate, th, kind, sample = _cpu_reference_rate(args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step, B=32 T=200 V=20001 (CPU port, host cores)"},
-            "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": th, "kind": "port", "sample": sample},
+            "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step, B=32 T=200 V=20001 (reference path, host cores)"},
+            "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": th, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_quick():
-    """~10-30 s of CPU work on a bounded sample of the same workload (rank 0, N=1 only)."""
-    rate, th, sample = _cpu_port_rate(3, 1, budget_s=20.0)
-    return {"value": rate, "unit": "steps/s", "cores": th, "kind": "port", "sample": sample}
+    """~10-30 s of CPU work: a bounded number of FULL steps of the reference path (rank 0, N=1 only)."""
+    rate, th, kind, sample = _cpu_reference_rate(3, 1, budget_s=25.0)
+    return {"value": rate, "unit": "steps/s", "cores": th, "kind": kind, "sample": sample}
 
 
-def torch_gpu_port(steps=6):
-    """The same port on THIS GPU through torch's stock cuDNN/cuBLAS path (what the unmodified reference
-    would run on a B200) — informational, the denominator of north_star's >=10x target."""
+def reference_same_gpu(steps=20):
+    """The reference's own modules on THIS GPU through torch's stock cuDNN/cuBLAS path (cudnn.deterministic as
+    text.py:102, default TF32 flags recorded) — the denominator of north_star's ">= 10x the reference single-GPU PyTorch
+    step time".  >= 20 timed steps, CUDA events, host inputs resident on the device as in the reference script."""
     import lagging_oracle as O
     c = CFG
-    torch.manual_seed(0)
-    m = O.FastPort(c["V"], c["ni"], c["nh"], c["nz"]).cuda().train()
     torch.backends.cudnn.deterministic = True         # text.py:102
+    m, kind = _reference_stepper("cuda")
     xs = [O.make_token_batch(c["B"], c["T"], c["V"], seed=99 + i).cuda() for i in range(4)]
     for i in range(3):
         m.inner_step(xs[i % 4], KL_WEIGHT)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for i in range(steps):
         m.inner_step(xs[i % 4], KL_WEIGHT)
+    e1.record()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / steps
     del m
     torch.cuda.empty_cache()
-    return {"value": steps / dt, "unit": "steps/s", "what": "oracle.FastPort (nn.LSTM/nn.Linear -> cuDNN/cuBLAS fp32) on this GPU",
+    return {"value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "kind": kind,
+            "what": ("the reference's own modules" if kind == "reference" else "oracle.FastPort") +
+                    " (nn.LSTM / nn.Linear / CrossEntropyLoss -> cuDNN / cuBLAS fp32, text.py:373-387 sequence) on this GPU",
             "tf32_matmul": bool(torch.backends.cuda.matmul.allow_tf32), "tf32_cudnn": bool(torch.backends.cudnn.allow_tf32)}
 
 
@@ -300,21 +326,31 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = lagvae.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step_fused(args.warmup + i)
-    e1.record()
-    barrier()
-    launches = lagvae.launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
-    n_timed_samples = len(sampler.rows)                # samples taken inside the timed region proper
+    # three repeats of EXACTLY K steps, each bracketed by barrier + synchronize on both sides and timed with CUDA events on
+    # the launching stream (max over ranks); `value` is the median repeat, all three are reported
+    rep_ms, launches, n_timed_samples = [], 0, 0
+    for rep in range(3):
+        barrier()
+        l0 = lagvae.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step_fused(args.warmup + (rep * args.steps + i) % (len(picks) - args.warmup))
+        e1.record()
+        barrier()
+        launches = lagvae.launch_count() - l0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rep_ms.append(float(ms))
+        if rep == 0:
+            n_timed_samples = len(sampler.rows)        # clock samples taken inside the first timed region proper
+    ms_total = float(np.median(rep_ms))
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total / 1e3)     # 32-sentence encoder steps per second, all ranks
+    variant = lagvae.lstm_variant()
+    if c["nh"] >= 256 and not (variant["forward"].startswith("v") and variant["backward"].startswith("v")):
+        raise RuntimeError("bench: the persistent recurrence kernels did not run (%r)" % (variant,))
 
     # ---------------- e2e: drop-in modules API, host token ids, per-step readback ----------------
     e2e = None
@@ -410,7 +446,10 @@ def run_ours(args, rank, world, local_rank):
             "step_tensor_frac": F / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peak)}
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3-split operands, f32 accumulate/state", "data": "synthetic",
+            "dtype": "bf16x3-split operands (hi*hi + hi*lo + lo*hi), f32 accumulate/state; in `value` the three decoder "
+                     "weight-gradient GEMMs (dW_pred, decoder dW_ih, dW_hh: never applied in the inner loop, they only enter "
+                     "the clip norm) run ONE bf16 pass; `e2e` runs all GEMMs 3-pass",
+            "data": "synthetic", "repeats_ms": rep_ms, "lstm_variant": variant,
             "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step (text.py:371-391), B=32/GPU T=200 V=20001 ni=512 nh=1024 nz=32, "
                                    "train-mode dropout 0.5/0.5, kl_weight 0.1, SGD lr 1.0, clip 5.0",
                        "global_batch": B * world, "parallelism": "dp%d" % world,
@@ -420,9 +459,12 @@ def run_ours(args, rank, world, local_rank):
             "flops_per_step": F, "algorithmic_tflops": F / (ms_per_step * 1e-3) / 1e12}
     if world == 1 and not args.no_cpu:
         try:
-            line["torch_gpu_port"] = torch_gpu_port()
-        except Exception as ex:  # informational only
-            line["torch_gpu_port"] = {"error": repr(ex)[:200]}
+            line["reference_same_gpu"] = reference_same_gpu()
+            line["speedup_vs_reference_same_gpu"] = {"value": value / line["reference_same_gpu"]["value"],
+                                                     "e2e": (e2e["value"] / line["reference_same_gpu"]["value"]) if e2e else None,
+                                                     "target": 10.0}
+        except Exception as ex:
+            line["reference_same_gpu"] = {"error": repr(ex)[:200]}
         line["cpu_baseline"] = cpu_baseline_quick()
     if world == 1 and not args.no_image:
         # informational: configs[3] (Omniglot ResNet encoder + PixelCNN decoder, batch 64) through the same drop-in API

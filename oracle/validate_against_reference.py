@@ -297,7 +297,7 @@ def run_big_case(ref, name, V, ni, nh, nz, B, T, klw, out_dir, train=False):
         for k, q in zip(O.ENC_KEYS, vae.encoder.parameters()):
             q = q.detach()
             out["postnorm." + k] = np.float64(q.double().norm())
-            out["postslice." + k] = q.reshape(-1)[:: max(1, q.numel() // 64)][:64].numpy()
+            out["postslice." + k] = q.reshape(-1)[:: max(1, q.numel() // 64)][:64].clone().numpy()   # clone: the values are restored below
             out["dnorm." + k] = np.float64((q - p0[k]).double().norm())     # size of the update itself
         vae.load_state_dict({**vae.state_dict(), **p0})
     vae.eval()

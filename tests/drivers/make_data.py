@@ -40,7 +40,7 @@ def make_text(root, n_train=160, n_val=48, n_test=48, seed=7):
     return d
 
 
-def make_image(root, n_train=250, n_val=50, n_test=50, seed=11):
+def make_image(root, n_train=250, n_val=50, n_test=500, seed=11):   # image.py:175 needs >= 10 test batches of 50
     import torch
     d = os.path.join(root, "datasets", "tinyomni_data")
     os.makedirs(d, exist_ok=True)

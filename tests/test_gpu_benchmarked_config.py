@@ -72,14 +72,16 @@ def test_yahoo_train_mode_reference_masks(golden):
     assert float(g["grad_norm"]) > 5.0            # the clip is active in this fixture
     norm = eng.clip_sgd(params, grads, 6, 5.0, 1.0)                                      # text.py:385,387
     assert abs(float(norm) - float(g["grad_norm"])) <= 1e-3 * float(g["grad_norm"])
+    coef = 5.0 / (float(g["grad_norm"]) + 1e-6)                                          # clip_grad_norm_ (A.5)
     for i, k in enumerate(O.ENC_KEYS):
         q = params[i]
         assert abs(float(q.double().norm()) - float(g["postnorm." + k])) <= 1e-5 * float(g["postnorm." + k]), k
         sl = q.reshape(-1)[:: max(1, q.numel() // 64)][:64].cpu()
-        # the update is small against the parameter: compare against the size of the update itself
-        upd = float(g["dnorm." + k]) / q.numel() ** 0.5
+        # post = p - coef * grad: the error budget is the gradient budget scaled by the clip coefficient (the embedding
+        # gradient is sparse, so a per-tensor RMS would be the wrong yardstick) plus fp32 rounding of the parameter
+        gscale = max(float(grads[i].abs().max()) * 0.05 / coef, float(np.abs(g["gslice." + k]).max()))
         err = float((sl - torch.from_numpy(g["postslice." + k])).abs().max())
-        assert err <= 5e-3 * max(upd, 1e-7) + 1e-6 * float(q.abs().max()), (k, err, upd)
+        assert err <= SLICE_TOL * coef * gscale + 2e-7 * float(q.abs().max()), (k, err, gscale)
     # MI on the original parameters (eval-mode forward, encoder.py:111-145)
     params = [p[k].cuda().contiguous() for k in O.ALL_KEYS]
     m2, l2 = eng.encode_stats(params, xc)
@@ -176,7 +178,9 @@ def test_lstm_v2_vs_float64_autograd(Bd, Tn):
     be.check(be.lib().lagvae_lstm_forward(1, nh, Tn, Bd, be.ptr(w_d), be.ptr(h0_d), be.ptr(c0_d), be.ptr(gates), be.ptr(c_all),
                                           be.ptr(h_all), be.ptr(hd), C.byref(drop), be.ptr(ws), ws.numel(), st), "lstm_forward")
     torch.cuda.synchronize()
-    assert lagvae.lstm_variant()["forward"].startswith("v2"), lagvae.lstm_variant()
+    # Bd = 128: the forward cluster kernel does not fit (128 KB resident W_hh + 72 KB receive slots + ring > 227 KB) and the
+    # dispatcher picks the persistent non-cluster kernel "v1" BY DESIGN — reported, not silent (lagvae_lstm_variant)
+    assert lagvae.lstm_variant()["forward"] == ("v2/cs2" if Bd <= 32 else "v1"), lagvae.lstm_variant()
     dc, dhr, dg = torch.zeros(Bd, nh, device="cuda"), torch.zeros(Bd, nh, device="cuda"), torch.zeros(Tn * Bd, 4 * nh, device="cuda")
     de, dl = dh_ext.reshape(Tn * Bd, nh).cuda().contiguous(), dh_last.cuda()
     be.check(be.lib().lagvae_lstm_backward(1, nh, Tn, Bd, be.ptr(w_d), be.ptr(c0_d), be.ptr(gates), be.ptr(c_all), be.ptr(de),

@@ -40,7 +40,8 @@ struct RecArgs {
   int part_bytes;                // bytes of one operand part of a ring stage = rows_alloc x 128 (rows_alloc = Bd rounded to 8, <= 64)
   unsigned long long* dbg;       // optional clock64 trace of CTA 0: [step][8]
   unsigned* bar;                 // grid barrier counter (host-zeroed)
-  __nv_bfloat16* abuf;           // [2 slots][2 parts][Bd][KP] streamed operand (h or dG), bf16 hi/lo
+  __nv_bfloat16* abuf;           // streamed operand (h or dG), bf16 hi/lo.  v1: [2 slots][2 parts][Bd][KP] (tensor-map view);
+                                 // v2: "tile image" [2 slots][KB k-blocks][m_tiles][2 parts][rows_alloc][128 B], see img_off()
   const float* w_hh;             // [4nh, nh]
   // forward
   const float* h0;
@@ -57,6 +58,7 @@ struct RecArgs {
   float* dh_rec_out;             // [Bd, nh] (d h_{-1}) when want_init
   float* dgates;                 // [Tn*Bd, 4nh]
   int want_init;
+  int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -93,6 +95,33 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 // swizzled (SWIZZLE_128B, K-major) byte offset of 16-byte chunk c of row r inside a tile of 128-B rows
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// v2 operand layout in GLOBAL memory = the shared-memory image of the ring stages: stage (kb, mt) is one contiguous block
+// [hi part rows ; lo part rows] x 128 B with SWIZZLE_128B already applied by the producing CTAs, so the consumer moves a
+// whole stage with ONE cp.async.bulk (no tensor map; a tensor-map box of 32 separate 128-B rows cost ~2.5 K cycles of
+// latency and ~10 B/clk per SM: profiles/r2a_exchange_probe_*.txt).  Byte offset inside a slot of the 16-B chunk that
+// holds K elements [k0, k0 + 8) of batch row b:
+__device__ __forceinline__ uint32_t img_off(int k0, int b, int part, int m_tiles, int rows_alloc) {
+  const int kb = k0 >> 6, c = (k0 & 63) >> 3, mt = b >> 6, r = b & 63;
+  return (uint32_t)((((kb * m_tiles + mt) * 2 + part) * rows_alloc + r) * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void store_bf16x4_img(uint8_t* slot, uint32_t off_hi, uint32_t off_lo, const float (&v)[4]) {
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+  uint2 h, l;
+  h.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+  h.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+  l.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+  l.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+  *(uint2*)(slot + off_hi) = h;
+  *(uint2*)(slot + off_lo) = l;
+}
 
 struct Smem {
   uint32_t w_base, a_base, bar_base;
@@ -565,7 +594,7 @@ struct V2Cfg {
 };
 
 template <bool FWD, int CS_>
-__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const __grid_constant__ TMaps tm) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
   using C = V2Cfg<FWD, CS_>;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,14 +647,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
   for (int i = threadIdx.x; i < nslots * rows_tot * C::RROW / 4; i += NTHREADS) st_shared_u4(r_base + 16u * i, RX_EMPTY);
   common_prologue(a, sm, tmem_cols, nullptr);
   const uint32_t tmem_base = *(uint32_t*)(gen_w + (sm.tmem_slot(a.NS) - sm.w_base));
-  const int64_t slot_elems = (int64_t)2 * Bd * a.KP;
+  const uint32_t stage_bytes = 2u * (uint32_t)a.part_bytes;
+  const size_t slot_bytes_g = (size_t)a.KB * a.m_tiles * stage_bytes;            // one operand slot in global memory
+  uint8_t* const abuf8 = (uint8_t*)a.abuf;
   if (FWD) {   // publish h_{-1} (own 8 units, all rows) into slot 1
     for (int b = threadIdx.x; b < Bd; b += NTHREADS) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = a.h0 ? a.h0[(int64_t)b * nh + u0 + j] : 0.f;
-      __nv_bfloat16* d = a.abuf + slot_elems + (int64_t)b * a.KP + u0;
-      store_bf16x8(d, d + (int64_t)Bd * a.KP, v);
+      uint8_t* slot = abuf8 + slot_bytes_g;
+      store_bf16x8((__nv_bfloat16*)(slot + img_off(u0, b, 0, a.m_tiles, rows_alloc)),
+                   (__nv_bfloat16*)(slot + img_off(u0, b, 1, a.m_tiles, rows_alloc)), v);
     }
   } else {
     for (int i = threadIdx.x; i < Bd * 8; i += NTHREADS) a.dc[(int64_t)(i >> 3) * nh + u0 + (i & 7)] = 0.f;
@@ -646,7 +678,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
     const int t = FWD ? s : Tn - 1 - s;              // backward: t = -1 on the extra step that only produces d h_{-1}
     const bool has_rec = FWD ? true : s > 0;
     const int rd_slot = (s + 1) & 1;
-    __nv_bfloat16* wr = a.abuf + (int64_t)(s & 1) * slot_elems;
+    uint8_t* const wr = abuf8 + (size_t)(s & 1) * slot_bytes_g;
     constexpr uint32_t idesc_all = ptx::make_idesc_bf16_f32(64, C::NALL, 0, 0);
     constexpr uint32_t idesc_hi = ptx::make_idesc_bf16_f32(64, C::NC, 0, 0);
 
@@ -707,10 +739,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
             ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
             const uint32_t sbase = sm.a_base + ps.stage * 2 * a.part_bytes;
             if (ptx::elect_one()) {
-              const int kx = ((int)rank * KBS + kb) * 64;
-              ptx::mbar_expect_tx(sm.full(ps.stage), 2u * (uint32_t)a.part_bytes);
-              ptx::tma_load_2d(sbase, &tm.m[rd_slot * 2 + 0], sm.full(ps.stage), kx, mt * 64);
-              ptx::tma_load_2d(sbase + a.part_bytes, &tm.m[rd_slot * 2 + 1], sm.full(ps.stage), kx, mt * 64);
+              const int kbg = (int)rank * KBS + kb;                       // k-block of the whole contraction
+              const uint8_t* src = abuf8 + (size_t)rd_slot * slot_bytes_g + (size_t)(kbg * a.m_tiles + mt) * stage_bytes;
+              ptx::mbar_expect_tx(sm.full(ps.stage), stage_bytes);
+              bulk_g2s(sbase, src, stage_bytes, sm.full(ps.stage));
             }
             __syncwarp();
             if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
@@ -880,12 +912,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
             hv[j] = og * ftanh(c);
             act[j] = ig; act[4 + j] = fg; act[8 + j] = gg; act[12 + j] = og;
           }
-          __nv_bfloat16* d = wr + (int64_t)b * a.KP + ub;
-          store_bf16x4(d, d + (int64_t)Bd * a.KP, hv);            // critical: operand of step s+1 on every SM
+          {                                                       // critical: operand of step s+1 on every SM
+            const uint32_t oh = img_off(ub & ~7, b, 0, a.m_tiles, rows_alloc) + (uint32_t)((ub & 4) << 1);
+            store_bf16x4_img(wr, oh, oh + (uint32_t)a.part_bytes, hv);
+          }
           if (!defer) store_rest(it);
         }
         if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();       // cell done, operand stores issued
-        ptx::fence_proxy_async_all();   // the operand of the next step is read by TMA (async proxy) on other SMs
+        // The operand of the next step is read through the async proxy (cp.async.bulk) on other SMs.  The generic->async proxy
+        // fence sits on the CONSUMER side only (TMA warp: acquire of the counter, then fence.proxy.async, then the copies): the
+        // release/acquire pair orders the generic stores before the acquire, the consumer's proxy fence orders its later
+        // async-proxy reads after it.  A second fence here waited for the store acknowledgements a second time (~1.4 K
+        // cycles per time step, profiles/r2a_exchange_probe_d0.txt P0 vs P1; data validated in the probe and by the tests).
+        if (a.prod_fence) ptx::fence_proxy_async_all();
         if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
         asm volatile("bar.sync 1, 128;" ::: "memory");                     // the 4 epilogue warps
         if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
@@ -947,17 +986,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a, const 
               dg[12 + j] = dh * tc * og * (1.f - og);
               dcn[j] = dct * fg;
             }
-            __nv_bfloat16* wb = wr + (int64_t)b * a.KP + ub;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {       // critical: operand of step s+1 on every SM
+            for (int q = 0; q < 4; ++q) {       // critical: operand of step s+1 on every SM (K index = gate q * nh + unit)
               float seg[4] = {dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]};
-              store_bf16x4(wb + q * nh, wb + q * nh + (int64_t)Bd * a.KP, seg);
+              const int k = q * nh + ub;
+              const uint32_t oh = img_off(k & ~7, b, 0, a.m_tiles, rows_alloc) + (uint32_t)((k & 4) << 1);
+              store_bf16x4_img(wr, oh, oh + (uint32_t)a.part_bytes, seg);
             }
           }
           if (!defer) store_rest(it);
         }
         if (trace && threadIdx.x == 0) a.dbg[s * 8 + 7] = clock64();
-        ptx::fence_proxy_async_all();
+        if (a.prod_fence) ptx::fence_proxy_async_all();          // see the forward branch
         if (trace && threadIdx.x == 0) a.dbg[s * 8 + 4] = clock64();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
@@ -1031,7 +1071,8 @@ static bool shape_supported(const lagvae_text_dims& d) {
 size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc) {
   if (!use_tc) return 0;
   const int64_t Bd = (int64_t)d.B * d.ns, KPb = round_up(4 * d.nh, 64);
-  return (size_t)(2 * 2 * Bd * KPb * 2 + 1024);   // sized for the backward operand (>= forward's)
+  const int64_t rows = Bd >= 64 ? round_up(Bd, 64) : round_up(Bd, 8);   // v2 tile image: whole row tiles per k-block
+  return (size_t)(2 * 2 * rows * KPb * 2 + 1024);   // sized for the backward operand (>= forward's)
 }
 
 int lstm_tc_create(const lagvae_text_dims& d, bool use_tc, void* ws, size_t ws_bytes, LstmTcState** out) {
@@ -1066,6 +1107,11 @@ static int configure(LstmTcState* s) {
   LV_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   s->configured = true;
   return LAGVAE_OK;
+}
+
+static int prod_fence_env() {
+  static const int v = [] { const char* e = getenv("LAGVAE_LSTM_PROD_FENCE"); return (e && e[0] == '1') ? 1 : 0; }();
+  return v;
 }
 
 // ---- v2 (cluster K-split) geometry / launch ---------------------------------------------------------------
@@ -1141,7 +1187,8 @@ static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, si
     stt = 1;
   }
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tm);
+  (void)tm;   // v2 reads its operand with cp.async.bulk from the tile-image layout: no tensor maps
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("lstm v2 (%s, cluster of %d) cooperative launch failed: %s", FWD ? "forward" : "backward", C::CS,
@@ -1187,6 +1234,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
     a.m_tiles = (int)cdiv(Bd, 64);
     LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
   }
+  a.prod_fence = prod_fence_env();
   a.dbg = (g_dbg && g_dbg_words >= (size_t)Tn * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
   a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
@@ -1239,6 +1287,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
     a.m_tiles = (int)cdiv(Bd, 64);
     LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
   }
+  a.prod_fence = prod_fence_env();
   a.dbg = (g_dbg && g_dbg_words >= (size_t)(Tn + 1) * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
   a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;
