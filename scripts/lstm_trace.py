@@ -17,12 +17,13 @@ w_hh = (torch.rand(4 * nh, nh, generator=g, device=dev) * 2 - 1) * (3.0 / nh ** 
 pre = torch.randn(Tn * Bd, 4 * nh, generator=g, device=dev)
 ws = torch.zeros(int(be.lib().lagvae_lstm_workspace_bytes(nh, Bd)), dtype=torch.uint8, device=dev)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-dbg = torch.zeros((Tn + 1) * 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(2 * (Tn + 1) * 8, dtype=torch.int64, device=dev)
 drop = be.Dropout()
 out = []
 
 
 def summarize(name, steps):
+    d2 = dbg.view(-1, 8)[Tn + 1:Tn + 1 + steps].cpu().double()
     d = dbg.view(-1, 8)[:steps].cpu().double()
     t0 = d[:, 0]
     per_step = (t0[1:] - t0[:-1])
@@ -36,6 +37,9 @@ def summarize(name, steps):
             continue                      # v1 kernels do not record the cluster phases
         out.append("   %-28s +%7.0f cycles (mean offset from step start)" % (n, float(c[sel].mean())))
     out.append("   %-28s +%7.0f cycles" % ("next step start", float(per_step[sel].mean())))
+    if float(d2.abs().max()) > 0:
+        for i, n in enumerate(["copy: epilogue at go-wait", "copy: go seen", "copy: all stages issued", "copy: all stages landed"]):
+            out.append("   %-32s %+7.0f cycles (vs step start)" % (n, float((d2[:, i] - d[:, 0])[sel].mean())))
 
 
 for rep in range(2):

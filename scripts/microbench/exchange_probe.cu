@@ -25,6 +25,14 @@
 //   P15 P6 but the 4 epilogue warps copy the slice with generic LDG.128 -> STS.128 (image layout == smem layout) and a
 //       CTA-local fence.proxy.async.shared::cta; no global proxy fence at all
 //   P16 P11 + P12: staggered start, 4 x 16 KB copies
+//   P20/P21/P22 = P9 / P15 / P6 with the operand written to 4 replicas (different addresses -> different L2 slices); a consumer
+//       reads replica (cta / 2) % 4: every line is read by 16 SMs instead of 64 (tests the L2 hot-spot hypothesis)
+//   P18 P15 while another warp spins on ld.acquire.gpu of the counter (next step's target) during the copy
+//   P19 P18 with the spinning warp using ld.relaxed.gpu + nanosleep(64)
+//   P17 validity-in-data: no counter, no release, no global fence.  Producers write whole 16-B chunks whose first bf16 carries
+//       a 1-bit tag in its LSB (tag = parity of the slot's reuse count, 4 slots); the 4 epilogue warps poll-load their K-slice
+//       with LDG.128 (L2), re-issue only the chunks whose tag is stale, store to shared memory (image layout == smem layout),
+//       fence.proxy.async.shared::cta, arrive.  Chain = store one-way + load round trip.
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o exchange_probe exchange_probe.cu
 // run  : ./exchange_probe [steps=400] [delay_cycles=0]
@@ -48,7 +56,7 @@ using namespace lagvae;
     }                                                                                             \
   } while (0)
 
-constexpr int G = 128, BD = 32, NH = 1024, KB = 8, NS = 8, NSLOT = 4;
+constexpr int G = 128, BD = 32, NH = 1024, KB = 8, NS = 8, NSLOT = 4, NREP = 4;
 constexpr int PART_BYTES = BD * 128;                 // one operand part of a ring stage: 32 rows x 128 B
 constexpr int NTHREADS = 192;
 
@@ -305,10 +313,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
 
   for (int s = 0; s <= a.steps; ++s) {
     if (s > 0) {
-      const uint8_t* src = gbase + (size_t)((s - 1) & (NSLOT - 1)) * SLOT_BYTES + (size_t)rank * KB * STAGE_BYTES;
+      constexpr bool REPL = (PROTO == 20 || PROTO == 21 || PROTO == 22);
+      const uint8_t* src = gbase + (size_t)((s - 1) & (NSLOT - 1)) * SLOT_BYTES + (size_t)rank * KB * STAGE_BYTES +
+                           (REPL ? (size_t)((blockIdx.x >> 1) & (NREP - 1)) * NSLOT * SLOT_BYTES : 0);
       if (warp == 5) {
-        if (PROTO == 15) {
+        if (PROTO == 15 || PROTO == 21) {
           // warp 5 idle: the epilogue warps do the copy below
+        } else if (PROTO == 18 || PROTO == 19) {
+          // warp 5 keeps polling the counter for the NEXT step while the epilogue warps copy (what k_lstm_v2's poller does)
+          if (lane == 0 && s < a.steps) {
+            const unsigned target = (unsigned)(s + 1) * per_step;
+            unsigned spins = 0;
+            if (PROTO == 18) {
+              while (ld_acquire_u32(rd_counter) < target) if (++spins > (1u << 24)) asm volatile("trap;");
+            } else {
+              unsigned v;
+              do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(rd_counter) : "memory");
+                if (v < target) __nanosleep(64);
+                if (++spins > (1u << 24)) asm volatile("trap;");
+              } while (v < target);
+            }
+          }
+          __syncwarp();
         } else if (PROTO != 8) {
           if (lane == 0) {
             const unsigned target = (unsigned)s * per_step;
@@ -320,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
           if (PROTO == 14) asm volatile("fence.proxy.async.global;" ::: "memory");
           else if (PROTO != 13) ptx::fence_proxy_async_all();
           if (tr && lane == 0) a.trace[s * 8 + 7] = clock64();
-          if (PROTO == 9) {
+          if (PROTO == 9 || PROTO == 20) {
             // one 64 KB copy: all NS = 8 stages are consecutive in the ring; stage 0's barrier carries the whole transaction
             for (int kb = 0; kb < KB; ++kb) ptx::mbar_wait(empty(kb), phase ^ 1u);
             if (ptx::elect_one()) {
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
           stage = st2; phase = ph2;
         } else {
           // stage index == k-block index; walk in the producer's order, group leaders carry the data barrier
-          const int GRP = (PROTO == 9) ? 8 : (PROTO == 12 ? 4 : (PROTO == 16 ? 2 : 1));
+          const int GRP = (PROTO == 9 || PROTO == 20) ? 8 : (PROTO == 12 ? 4 : (PROTO == 16 ? 2 : 1));
           const int start = (PROTO == 11) ? ((blockIdx.x >> 1) & 7) : (PROTO == 16 ? (((blockIdx.x >> 1) & 7) & ~(GRP - 1)) : 0);
           for (int i = 0; i < KB; ++i) {
             const int kb = (start + i) & 7;
@@ -432,7 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
         }
         if (tr && lane == 0) a.trace[s * 8 + 3] = clock64();
         if (lane == 0) ptx::mbar_arrive(done_bar);
-      } else if (PROTO == 15) {
+      } else if (PROTO == 15 || PROTO == 18 || PROTO == 19 || PROTO == 21) {
         // epilogue warps: generic-proxy copy of the 64 KB slice (image layout == shared-memory layout)
         if (threadIdx.x == 0) {
           const unsigned target = (unsigned)s * per_step;
@@ -478,8 +505,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
         lo.x = bf16_bits(s, 1, b, ub) | ((uint32_t)bf16_bits(s, 1, b, ub + 1) << 16);
         lo.y = bf16_bits(s, 1, b, ub + 2) | ((uint32_t)bf16_bits(s, 1, b, ub + 3) << 16);
         const uint32_t off = (uint32_t)(b * 128 + ((c ^ (b & 7)) << 4) + uq * 8);
-        *(uint2*)(wslot + off) = hi;
-        *(uint2*)(wslot + PART_BYTES + off) = lo;
+        constexpr bool REPLW = (PROTO == 20 || PROTO == 21 || PROTO == 22);
+#pragma unroll
+        for (int r = 0; r < (REPLW ? NREP : 1); ++r) {
+          *(uint2*)(wslot + (size_t)r * NSLOT * SLOT_BYTES + off) = hi;
+          *(uint2*)(wslot + (size_t)r * NSLOT * SLOT_BYTES + PART_BYTES + off) = lo;
+        }
       }
       if (tr && threadIdx.x == 0) a.trace[s * 8 + 5] = clock64();
       if (PROTO == 10) {
@@ -498,6 +529,112 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe2(const Args a) {
           if (tr) a.trace[s * 8 + 6] = clock64();
         }
       }
+    }
+  }
+  if (errs) atomicAdd(a.errors, errs);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// P17: validity-in-data ("tagged chunks")
+__device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(NTHREADS, 1) k_probe3(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t bars = base + NS * 2 * PART_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  const uint32_t done_bar = bars + 8u * (2 * NS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = blockIdx.x & 1, u0 = blockIdx.x * 8;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) ptx::mbar_init(full(s), 128);
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  constexpr size_t SLOT_BYTES = (size_t)16 * 2 * PART_BYTES;
+  constexpr uint32_t STAGE_BYTES = 2 * PART_BYTES;
+  uint8_t* gbase = (uint8_t*)a.abuf;
+  const bool tr = a.trace != nullptr && blockIdx.x == 0;
+  unsigned errs = 0;
+  uint32_t phase = 0;
+  for (int s = 0; s <= a.steps; ++s) {
+    if (s > 0) {
+      const int pidx = s - 1;                                             // publish index of the data read now
+      const uint32_t want = (uint32_t)(((pidx / NSLOT) + 1) & 1);
+      const uint8_t* src = gbase + (size_t)(pidx & (NSLOT - 1)) * SLOT_BYTES + (size_t)rank * KB * STAGE_BYTES;
+      if (warp < 4) {
+        const uint4* g4 = (const uint4*)src;
+        uint4* s4 = (uint4*)gen;
+        unsigned spins = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = ld_cg_u4(g4 + (h * 16 + j) * 128 + threadIdx.x);
+          bool all_ok;
+          do {
+            all_ok = true;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((v[j].x & 1u) != want) {
+                v[j] = ld_cg_u4(g4 + (h * 16 + j) * 128 + threadIdx.x);
+                all_ok = false;
+              }
+            if (++spins > (1u << 22)) asm volatile("trap;");
+          } while (!all_ok);
+          if (tr && threadIdx.x == 0 && h == 0) a.trace[s * 8 + 1] = clock64();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s4[(h * 16 + j) * 128 + threadIdx.x] = v[j];
+          ptx::fence_proxy_async_smem();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ptx::mbar_arrive(full(h * 4 + j));   // 4 chunks of this thread per stage: stage = (h*16 + j) / 4
+        }
+      } else if (warp == 4) {
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(full(kb), phase);
+          if (tr && lane == 0 && kb == 0) a.trace[s * 8 + 2] = clock64();
+          for (int part = 0; part < 2; ++part) {
+            const uint8_t* tile = gen + (kb * STAGE_BYTES + part * PART_BYTES);
+            const int c = 3;
+            const uint4 v = *(const uint4*)(tile + lane * 128 + ((c ^ (lane & 7)) << 4));
+            const int ug = (rank * KB + kb) * 64 + c * 8;
+            if ((unsigned short)((v.x & 0xfffe)) != (bf16_bits(s - 1, part, lane, ug) & 0xfffe)) ++errs;
+          }
+          __syncwarp();
+        }
+        phase ^= 1u;
+        if (tr && lane == 0) a.trace[s * 8 + 3] = clock64();
+        if (lane == 0) ptx::mbar_arrive(done_bar);
+      }
+      if (warp < 4) ptx::mbar_wait(done_bar, (uint32_t)((s - 1) & 1));
+    }
+    if (s == a.steps) break;
+    if (warp < 4) {
+      if (a.delay > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.delay) {
+        }
+      }
+      if (tr && threadIdx.x == 0) a.trace[s * 8 + 4] = clock64();
+      const int pidx = s;                                                 // publish index
+      const uint32_t tag = (uint32_t)(((pidx / NSLOT) + 1) & 1);
+      uint8_t* wslot = gbase + (size_t)(pidx & (NSLOT - 1)) * SLOT_BYTES + (size_t)(blockIdx.x / 8) * STAGE_BYTES;
+      const int c = blockIdx.x & 7;
+      if (threadIdx.x < 64) {        // thread = (row b, part): one whole 16-B chunk each
+        const int b = threadIdx.x >> 1, part = threadIdx.x & 1;
+        uint4 v;
+        v.x = ((bf16_bits(s, part, b, u0) & 0xfffe) | tag) | ((uint32_t)bf16_bits(s, part, b, u0 + 1) << 16);
+        v.y = bf16_bits(s, part, b, u0 + 2) | ((uint32_t)bf16_bits(s, part, b, u0 + 3) << 16);
+        v.z = bf16_bits(s, part, b, u0 + 4) | ((uint32_t)bf16_bits(s, part, b, u0 + 5) << 16);
+        v.w = bf16_bits(s, part, b, u0 + 6) | ((uint32_t)bf16_bits(s, part, b, u0 + 7) << 16);
+        *(uint4*)(wslot + part * PART_BYTES + b * 128 + ((c ^ (b & 7)) << 4)) = v;
+      }
+      if (tr && threadIdx.x == 0) { a.trace[s * 8 + 5] = clock64(); a.trace[s * 8 + 6] = clock64(); }
     }
   }
   if (errs) atomicAdd(a.errors, errs);
@@ -526,10 +663,12 @@ static void make_map(CUtensorMap* m, void* basep, uint32_t box_cols, uint32_t bo
   if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
 }
 
+static size_t g_smem_pad = 0;   // extra dynamic shared memory (shrinks the L1: the real kernel runs at the 227 KB carve-out)
 template <int PROTO, bool V2 = false>
 static void run(const char* name, Args a, const Maps& tm, int steps) {
-  const size_t smem = NS * 2 * PART_BYTES + 1024 + 8 * (2 * NS + 2) + 1024 + 64;
-  const void* kfn = V2 ? (const void*)k_probe2<PROTO> : (const void*)k_probe<PROTO>;
+  const size_t smem = NS * 2 * PART_BYTES + 1024 + 8 * (2 * NS + 2) + 1024 + 64 + g_smem_pad;
+  const void* kfn = PROTO == 17 ? (const void*)k_probe3 : (V2 ? (const void*)k_probe2<PROTO> : (const void*)k_probe<PROTO>);
+  if (PROTO == 17) CK(cudaMemset(a.abuf, 0, (size_t)NSLOT * 2 * BD * NH * 2));
   CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -577,11 +716,12 @@ static void run(const char* name, Args a, const Maps& tm, int steps) {
 int main(int argc, char** argv) {
   const int steps = argc > 1 ? atoi(argv[1]) : 400;
   const int delay = argc > 2 ? atoi(argv[2]) : 0;
+  g_smem_pad = argc > 3 ? (size_t)atoi(argv[3]) * 1024 : 0;
   Args a{};
   a.steps = steps;
   a.delay = delay;
-  CK(cudaMalloc(&a.abuf, (size_t)NSLOT * 2 * BD * NH * 2));
-  CK(cudaMemset(a.abuf, 0, (size_t)NSLOT * 2 * BD * NH * 2));
+  CK(cudaMalloc(&a.abuf, (size_t)NREP * NSLOT * 2 * BD * NH * 2));
+  CK(cudaMemset(a.abuf, 0, (size_t)NREP * NSLOT * 2 * BD * NH * 2));
   CK(cudaMalloc(&a.counter, 256));
   CK(cudaMalloc(&a.flags, G * 4));
   CK(cudaMalloc(&a.errors, 4));
@@ -595,7 +735,8 @@ int main(int argc, char** argv) {
     }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
-  printf("device %s, %d SMs, steps %d, simulated compute delay %d cycles\n", prop.name, prop.multiProcessorCount, steps, delay);
+  printf("device %s, %d SMs, steps %d, simulated compute delay %d cycles, smem pad %zu KB\n", prop.name, prop.multiProcessorCount, steps, delay,
+         g_smem_pad >> 10);
   run<0>("P0 counter + both proxy fences (current)", a, tm, steps);
   run<1>("P1 counter, consumer-side proxy fence only", a, tm, steps);
   run<2>("P2 per-CTA flags, TMA per ready k-block", a, tm, steps);
@@ -613,5 +754,11 @@ int main(int argc, char** argv) {
   run<14, true>("P14 P6 with fence.proxy.async.global", a, tm, steps);
   run<15, true>("P15 generic LDG->STS copy by 4 warps", a, tm, steps);
   run<16, true>("P16 staggered start, 4 x 16KB copies", a, tm, steps);
+  run<17, true>("P17 validity-in-data, LDG poll by 4 warps", a, tm, steps);
+  run<20, true>("P20 P9 (1 x 64KB bulk) + 4 replicas", a, tm, steps);
+  run<21, true>("P21 P15 (LDG copy) + 4 replicas", a, tm, steps);
+  run<22, true>("P22 P6 (8 x 8KB bulk) + 4 replicas", a, tm, steps);
+  run<18, true>("P18 P15 + concurrent ld.acquire spinner", a, tm, steps);
+  run<19, true>("P19 P15 + relaxed/nanosleep spinner", a, tm, steps);
   return 0;
 }

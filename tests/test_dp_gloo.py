@@ -3,6 +3,7 @@ the single-process step on the full batch (exact reference semantics under batch
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -141,3 +142,93 @@ def test_micro_batch_accumulation_equals_full_batch(B, chunk):
     assert abs(norm - r["grad_norm"]) <= 1e-5 * r["grad_norm"] and r["coef"] < 1.0
     for k, got in zip(O.ENC_KEYS, params[:6]):
         assert float((got - p[k]).abs().max()) <= 1e-6 * max(1.0, float(p[k].abs().max())), k
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# b3: VAE.loss sharded inside the boundary (lagvae.dp.ShardedTextLoss) — the statement sequence of text.py:379-387 run SPMD
+class OracleEngine:
+    """CPU stand-in for lagvae.TextEngine (test-only): same loss_forward / loss_backward contract, oracle arithmetic."""
+
+    def __init__(self, two_buckets):
+        self.generation = 0
+        if two_buckets:
+            self.decoder_offset = None      # set by the worker once the parameter sizes are known
+
+    def loss_forward(self, params, x, eps, kl_weight, drop):
+        import lagging_oracle as O
+        self.generation += 1
+        with torch.enable_grad():          # called from inside an autograd.Function.forward (grad mode off there)
+            self._leaves = {k: p.detach().clone().requires_grad_(True) for k, p in zip(O.ALL_KEYS, params)}
+            self._out = O.vae_loss(self._leaves, x, kl_weight, eps)
+        return tuple(t.detach() for t in self._out)
+
+    def loss_backward(self, params, x, g_loss, g_rec, g_kl, generation=None, grads_out=None):
+        import lagging_oracle as O
+        assert generation == self.generation
+        with torch.enable_grad():
+            obj = sum((o * g).sum() for o, g in zip(self._out, (g_loss, g_rec, g_kl)) if g is not None)
+        obj.backward()
+        for k, dst in zip(O.ALL_KEYS, grads_out):
+            g = self._leaves[k].grad
+            g = torch.zeros_like(self._leaves[k]) if g is None else g.clone()
+            if k == "decoder.embed.weight":
+                g[-1].zero_()
+            dst.copy_(g)
+        return grads_out
+
+
+def _sharded_worker(rank, world, port, B, out_q, two_buckets):
+    _setup_path()
+    import lagging_oracle as O
+    from lagvae.dp import ShardedTextLoss
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, ni, nh, nz, T = 60, 6, 8, 2, 5
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=4))
+    params = [p[k].clone().requires_grad_(True) for k in O.ALL_KEYS]
+    x = O.make_token_batch(B, T, V)                       # SPMD: every rank holds the full batch and the same eps
+    eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
+    eng = OracleEngine(two_buckets)
+    if two_buckets:
+        eng.decoder_offset = sum(q.numel() for q in params[:6])
+    loss, rec, kl = ShardedTextLoss.apply(eng, dist.group.WORLD, x, 0.5, eps, lambda lo, hi: None, *params)
+    s = loss.sum().item()                                 # text.py:381
+    loss.mean(dim=-1).backward()                          # text.py:382-384
+    norm = float(torch.nn.utils.clip_grad_norm_(params, 0.05))    # text.py:385 (threshold scaled to the toy gradients)
+    torch.optim.SGD(params[:6], lr=1.0).step()            # text.py:387
+    out_q.put((rank, s, norm, loss.detach().numpy().copy(), rec.detach().numpy().copy(), kl.detach().numpy().copy(),
+               [q.detach().numpy().copy() for q in params[:6]], [q.grad.numpy().copy() for q in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,two_buckets", [(6, False), (5, True), (1, True)])
+def test_sharded_vae_loss_equals_single_process(B, two_buckets):
+    """The driver's statement sequence over ShardedTextLoss on 2 gloo ranks (even, ragged, empty shard) == the single-process
+    oracle step: full [B] loss vectors on every rank, gradient of the global mean, clip norm, encoder update."""
+    _setup_path()
+    import lagging_oracle as O
+    world, port = 2, 31000 + os.getpid() % 2000 + B + (10 if two_buckets else 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, B, q, two_buckets)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    V, ni, nh, nz, T = 60, 6, 8, 2, 5
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=4))
+    x = O.make_token_batch(B, T, V)
+    eps = torch.randn(B, 1, nz, generator=torch.Generator().manual_seed(9))
+    r = O.inner_step(p, x, 0.5, eps, max_norm=0.05, update=True)
+    for rank, s, norm, loss, rec, kl, enc, grads in res:
+        assert abs(s - r["loss_sum"]) <= 1e-5 * abs(r["loss_sum"])
+        assert np.allclose(loss, r["loss"].numpy(), rtol=1e-5, atol=1e-6) and loss.shape == (B,)
+        assert np.allclose(rec, r["rec"].numpy(), rtol=1e-5, atol=1e-6) and np.allclose(kl, r["kl"].numpy(), rtol=1e-4, atol=1e-6)
+        assert abs(norm - r["grad_norm"]) <= 1e-5 * r["grad_norm"] and r["coef"] < 1.0
+        for k, got in zip(O.ENC_KEYS, enc):
+            assert float(np.abs(got - p[k].numpy()).max()) <= 1e-6 * max(1.0, float(p[k].abs().max())), k
+    for a, b in zip(res[0][7], res[1][7]):                 # identical gradients on both ranks: replicas stay in lock step
+        assert np.array_equal(a, b)

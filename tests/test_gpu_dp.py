@@ -1,0 +1,119 @@
+"""Data parallelism inside the boundary on real GPUs: 2 ranks over NCCL run the driver's statement
+sequence (text.py:379-387) on the SAME full batch through the drop-in `modules.VAE`; `VAE.loss` shards the batch by rank,
+returns the full [B] vectors and all-reduces the flat gradient bucket in its backward (decoder bucket on a side stream
+under the encoder backward).  Checked against the single-GPU run of the same modules on the same inputs (rank 0,
+LAGVAE_DP=0): loss / rec / KL vectors, all 13 gradients, clip norm, post-step encoder parameters; and both ranks end with
+bit-identical parameters.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on the 1-GPU box."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Vocab(dict):
+    def __init__(self, V):
+        super().__init__()
+        self.V = V
+        self["<s>"], self["</s>"] = 1, 2
+
+    def __len__(self):
+        return self.V
+
+    def id2word(self, i):
+        return str(i)
+
+
+def _build(V, ni, nh, nz, dev, p):
+    import modules
+    import lagging_oracle as O
+    a = types.SimpleNamespace(ni=ni, enc_nh=nh, dec_nh=nh, nz=nz, dec_dropout_in=0.5, dec_dropout_out=0.5, device=dev)
+    init = lambda t: torch.nn.init.uniform_(t, -0.01, 0.01)
+    vae = modules.VAE(modules.LSTMEncoder(a, V, init, init), modules.LSTMDecoder(a, _Vocab(V), init, init), a).to(dev)
+    sd = vae.state_dict()
+    sd.update({k: p[k].to(dev) for k in O.ALL_KEYS})
+    vae.load_state_dict(sd)
+    return vae.eval()          # eval(): no dropout, so the sharded and the single-device run are comparable element-wise
+
+
+def _driver_step(vae, x, klw):
+    enc_opt = torch.optim.SGD(vae.encoder.parameters(), lr=1.0, momentum=0)
+    dec_opt = torch.optim.SGD(vae.decoder.parameters(), lr=1.0, momentum=0)
+    enc_opt.zero_grad()
+    dec_opt.zero_grad()
+    loss, rec, kl = vae.loss(x, klw, nsamples=1)          # text.py:379
+    s = loss.sum().item()                                 # text.py:381
+    loss.mean(dim=-1).backward()                          # text.py:382-384
+    grads = [q.grad.detach().clone() for q in vae.parameters() if q.grad is not None]
+    norm = float(torch.nn.utils.clip_grad_norm_(vae.parameters(), 5.0))   # text.py:385
+    enc_opt.step()                                        # text.py:387
+    return s, loss.detach(), rec.detach(), kl.detach(), grads, norm
+
+
+def _worker(rank, world, port, shape, out_q):
+    for p_ in (os.path.join(ROOT, "vae-lagging-encoder_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p_)
+    import torch.distributed as dist
+    import lagging_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    V, ni, nh, nz, B, T = shape
+    p = O.scale_trained_like(O.init_text_params(V, ni, nh, nz, seed=3), 4.0)
+    x = O.make_token_batch(B, T, V).to(dev)
+    res = {}
+    for mode in ("dp", "single"):
+        if mode == "single" and rank != 0:
+            continue
+        os.environ["LAGVAE_DP"] = "1" if mode == "dp" else "0"
+        vae = _build(V, ni, nh, nz, dev, p)
+        torch.manual_seed(1234)                           # identical eps draw on every rank (SPMD)
+        torch.cuda.manual_seed(1234)
+        s, loss, rec, kl, grads, norm = _driver_step(vae, x, 0.3)
+        torch.cuda.synchronize()
+        res[mode] = (s, loss.cpu(), rec.cpu(), kl.cpu(), [g.cpu() for g in grads], norm,
+                     [q.detach().cpu() for q in vae.encoder.parameters()])
+    os.environ["LAGVAE_DP"] = "1"
+    out_q.put((rank, {k: (v[0], v[1].numpy(), v[2].numpy(), v[3].numpy(), [g.numpy() for g in v[4]], v[5], [q.numpy() for q in v[6]])
+                      for k, v in res.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(520, 64, 256, 8, 16, 10), (520, 64, 256, 8, 5, 9), (20001, 512, 1024, 32, 32, 50)],
+                         ids=["even", "ragged", "yahoo-dims-T50"])
+def test_two_gpu_sharded_vae_loss_matches_single_gpu(shape):
+    import numpy as np
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world, port = 2, 33000 + os.getpid() % 2000 + shape[4]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    one = res[0]["single"]
+    for rank in range(world):
+        s, loss, rec, kl, grads, norm, enc = res[rank]["dp"]
+        assert abs(s - one[0]) <= 1e-5 * abs(one[0])
+        assert np.allclose(loss, one[1], rtol=2e-5, atol=1e-5) and loss.shape == (shape[4],)
+        assert np.allclose(rec, one[2], rtol=2e-5, atol=1e-5) and np.allclose(kl, one[3], rtol=1e-4, atol=1e-5)
+        assert abs(norm - one[5]) <= 1e-4 * one[5]
+        for a, b in zip(grads, one[4]):
+            assert float(np.abs(a - b).max()) <= 2e-4 * max(float(np.abs(b).max()), 1e-7)   # different summation split only
+        for a, b in zip(enc, one[6]):
+            assert float(np.abs(a - b).max()) <= 1e-5 * max(float(np.abs(b).max()), 1e-7)
+    for a, b in zip(res[0]["dp"][6], res[1]["dp"][6]):
+        assert np.array_equal(a, b)                       # replicas stay bit-identical without a parameter broadcast
+    for a, b in zip(res[0]["dp"][4], res[1]["dp"][4]):
+        assert np.array_equal(a, b)

@@ -58,6 +58,7 @@ struct RecArgs {
   float* dh_rec_out;             // [Bd, nh] (d h_{-1}) when want_init
   float* dgates;                 // [Tn*Bd, 4nh]
   int want_init;
+  int bulk_stages;               // v2: ring stages per cp.async.bulk copy (LAGVAE_LSTM_BULK_STAGES, default 4)
   int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
 };
 
@@ -222,13 +223,14 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst_hi, __nv_bfloat1
   *(uint4*)dst_lo = *(const uint4*)lo;
 }
 
-__device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm, int tmem_cols, uint32_t* slot_ptr) {
+__device__ __forceinline__ void common_prologue(const RecArgs& a, const Smem& sm, int tmem_cols, uint32_t* slot_ptr,
+                                                uint32_t full_count = 1) {
   const int warp = threadIdx.x >> 5;
   // ring rows beyond the batch are never written: the UMMA reads 64 rows, but D row i depends on A row i only and
   // rows >= Bd of D are never read back, so whatever aliases there (next part / next stage / W tiles) is harmless
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.NS; ++s) {
-      ptx::mbar_init(sm.full(s), 1);
+      ptx::mbar_init(sm.full(s), full_count);
       ptx::mbar_init(sm.empty(s, a.NS), 1);
     }
     for (int m = 0; m < MAX_MT; ++m) ptx::mbar_init(sm.acc(m, a.NS), 1);
@@ -583,6 +585,14 @@ __device__ __forceinline__ bool rx_ready(const float4& v) {
          __float_as_uint(v.w) != RX_EMPTY;
 }
 
+// v2 operand load: the 4 epilogue warps (idle until the accumulators complete) copy the CTA's K slice of the published
+// operand from global memory (L2) into the ring with plain 16-byte loads and stores — the global tile image IS the
+// shared-memory image — G stages (16 chunks per thread) in flight at a time, then a CTA-local generic->async proxy fence
+// and one mbarrier arrival per stage for the MMA warp.  Measured against cp.async.bulk / tensor TMA for this access
+// pattern (128 CTAs pulling 64 KB each out of the same 128 KB every ~6 us; profiles/r2b_exchange_probe_*.txt): the bulk
+// copies cost ~2.3 K cycles to the first byte plus ~0.7 K per 8 KB copy (P6: 10.2 K cycles per exchange) against ~2.0 K
+// cycles for the whole 64 KB with LDG.128 (P15: 6.5 K), and a global-scope fence.proxy.async (724 cycles) disappears
+// because no async-proxy operation reads global memory any more.
 template <bool FWD, int CS_>
 struct V2Cfg {
   static constexpr int CS = CS_;                  // cluster size = K split (forward 4; backward 8, or 4 when 16 clusters of 8 do not fit)
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
   cluster_sync_all();                                // peers' smem (receive slots, barriers) exist before any DSMEM access
   grid_barrier(a.bar, gridDim.x);                    // epoch 1: initial operand published; step s ends epoch s + 2
 
-  PipeState ps{0, 0};
+  PipeState ps{0, 0};      // ring position (producer warp and MMA warp each advance their own copy)
   const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   const int nsteps = FWD ? Tn : Tn + (a.want_init ? 1 : 0);
   int acc_par = 0;
@@ -719,13 +729,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
         }
       }
     };
-    if (warp < 4 && (int)threadIdx.x < items) load_inputs((int)threadIdx.x);
-
     if (warp == 5) {
-      // ------------------------------- TMA producer: this CTA's K slice of the streamed operand
-      if (s > 0) {                       // every CTA has stored its part of this step's operand
+      // ------------------------------- producer: this CTA's K slice of the published operand, global (L2) -> ring
+      if (s > 0) {                       // every CTA has published its part of this step's operand
         if (lane == 0) {
           const unsigned target = (unsigned)(s + 1) * gridDim.x;
+          // (measured and rejected, profiles/README.md r2c: pipelined polls — 4 relaxed loads in flight, one every 160 cycles —
+          // made the step 17 % SLOWER, the extra requests queue in front of the arrivals on the counter's L2 line; sleeping
+          // 1-4 us before the first poll changed nothing)
           while (ld_acquire_u32(a.bar) < target) {
           }
         }
@@ -733,33 +744,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
       }
       if (trace && lane == 0) a.dbg[s * 8 + 0] = clock64();   // step start = grid counter complete
       if (has_rec) {
-        ptx::fence_proxy_async_all();
-        for (int mt = 0; mt < a.m_tiles; ++mt)
-          for (int kb = 0; kb < KBS; ++kb) {
-            ptx::mbar_wait(sm.empty(ps.stage, a.NS), ps.phase ^ 1u);
-            const uint32_t sbase = sm.a_base + ps.stage * 2 * a.part_bytes;
-            if (ptx::elect_one()) {
-              const int kbg = (int)rank * KBS + kb;                       // k-block of the whole contraction
-              const uint8_t* src = abuf8 + (size_t)rd_slot * slot_bytes_g + (size_t)(kbg * a.m_tiles + mt) * stage_bytes;
-              ptx::mbar_expect_tx(sm.full(ps.stage), stage_bytes);
-              bulk_g2s(sbase, src, stage_bytes, sm.full(ps.stage));
-            }
-            __syncwarp();
-            if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+        // The operand was written with generic stores by other SMs (ordered before this point by their release and the
+        // acquire above) and is read through the async proxy: ONE consumer-side proxy fence, restricted to the global
+        // state space (fence.proxy.async over all state spaces: 724 cycles; .global: 20 — profiles/r2b_exchange_probe_d0.txt).
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        // The K slice of this CTA is ONE contiguous region of the tile image (k-block major: stage i = kb * m_tiles + mt).  It
+        // moves as a few LARGE cp.async.bulk copies of `a.bulk_stages` ring stages each: on this access pattern a bulk copy
+        // costs ~1.6 K cycles to its first byte and separate 8 KB copies retire one every ~0.7 K cycles, while 32 KB
+        // copies stream (probe P6 vs P12/P9).  The first stage of a group carries the group's transaction bytes; the MMA warp
+        // consumes stages in order, so it has passed the leader's barrier before it touches a later stage of the group.
+        const int nst = KBS * a.m_tiles;
+        const uint8_t* gsrc = abuf8 + (size_t)rd_slot * slot_bytes_g + (size_t)rank * nst * stage_bytes;
+        for (int i = 0; i < nst;) {
+          const int glen = min(min(a.bulk_stages, nst - i), a.NS - ps.stage);     // contiguous in the ring, too
+          for (int j = 0; j < glen; ++j) {
+            int slot = ps.stage + j;                                           // no wrap inside a group
+            ptx::mbar_wait(sm.empty(slot, a.NS), ps.phase ^ 1u);
           }
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(sm.full(ps.stage), (uint32_t)glen * stage_bytes);
+            bulk_g2s(sm.a_base + (uint32_t)ps.stage * stage_bytes, gsrc + (size_t)i * stage_bytes, (uint32_t)glen * stage_bytes,
+                     sm.full(ps.stage));
+            for (int j = 1; j < glen; ++j) ptx::mbar_arrive(sm.full(ps.stage + j));
+          }
+          __syncwarp();
+          i += glen;
+          ps.stage += glen;
+          if (ps.stage >= a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+        }
       }
     } else if (warp == 4) {
       // ------------------------------- MMA issuer: 2 instructions per K sub-step (see mma_pass)
       if (has_rec) {
-        for (int mt = 0; mt < a.m_tiles; ++mt) {
-          const uint32_t d = tmem_base + (uint32_t)(mt * C::NALL);
-          for (int kb = 0; kb < KBS; ++kb) {
-            ptx::mbar_wait(sm.full(ps.stage), ps.phase);
-            ptx::tc_fence_after();
-            if (trace && kb == 0 && mt == 0 && lane == 0) a.dbg[s * 8 + 1] = clock64();
-            const uint32_t sa = sm.a_base + ps.stage * 2 * a.part_bytes;
-            const uint32_t sw = sm.w_base + (uint32_t)kb * C::WT;
-            if (ptx::elect_one()) {
+        // Stages in k-block major order (stage i = kb * m_tiles + mt, the order of the tile image; each m-tile has its own
+        // accumulator), consumed in the producer's GROUPS: one barrier wait + one tcgen05 fence per group, then all its MMAs
+        // back to back.  tcgen05.mma issue is synchronous with the tensor pipe (no deep queue): every cycle the issuing
+        // thread spends between two MMAs is a cycle the pipe idles, and the per-stage wait / fence / elect / commit sequence
+        // cost ~250 cycles per 4 MMAs (measured: 127 cycles per M=64 N=128 MMA in the loop against 64 back to back).
+        const int nst = KBS * a.m_tiles;
+        for (int i = 0; i < nst;) {
+          const int glen = min(min(a.bulk_stages, nst - i), a.NS - ps.stage);
+          ptx::mbar_wait(sm.full(ps.stage), ps.phase);            // the group leader's barrier carries the group's bytes
+          ptx::tc_fence_after();
+          if (trace && i == 0 && lane == 0) a.dbg[s * 8 + 1] = clock64();
+          if (ptx::elect_one()) {
+            for (int j = 0; j < glen; ++j) {
+              const int kb = (i + j) / a.m_tiles, mt = (i + j) - kb * a.m_tiles;
+              const uint32_t d = tmem_base + (uint32_t)(mt * C::NALL);
+              const uint32_t sa = sm.a_base + (uint32_t)(ps.stage + j) * 2 * a.part_bytes;
+              const uint32_t sw = sm.w_base + (uint32_t)kb * C::WT;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
@@ -768,17 +801,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
                 ptx::umma_f16(d, a_hi, bdsc, idesc_all, (kb | k) ? 1u : 0u);
                 if (!stack) ptx::umma_f16(d, a_lo, bdsc, idesc_hi, 1u);
               }
-              ptx::umma_commit(sm.empty(ps.stage, a.NS));
-              if (kb == KBS - 1) ptx::umma_commit(sm.acc(mt, a.NS));
             }
-            __syncwarp();
-            if (++ps.stage == a.NS) { ps.stage = 0; ps.phase ^= 1u; }
+            for (int j = 0; j < glen; ++j) {
+              ptx::umma_commit(sm.empty(ps.stage + j, a.NS));
+              const int kb = (i + j) / a.m_tiles;
+              if (kb == KBS - 1) ptx::umma_commit(sm.acc((i + j) - kb * a.m_tiles, a.NS));
+            }
           }
+          __syncwarp();
+          i += glen;
+          ps.stage += glen;
+          if (ps.stage >= a.NS) { ps.stage = 0; ps.phase ^= 1u; }
         }
         if (trace && lane == 0) a.dbg[s * 8 + 2] = clock64();
       }
     } else {
       // =============================== epilogue warps 0-3 ===============================
+      if ((int)threadIdx.x < items) load_inputs((int)threadIdx.x);   // L2 latency hides under the MMAs
       if (has_rec) {
         // ---- part 1: partial products TMEM -> registers -> PUSH to the owner's receive slot (DSMEM store)
         const int nrow_mma = stack ? 2 * rows_alloc : rows_alloc;          // MMA rows of an m-tile that carry data
@@ -1024,7 +1063,7 @@ struct LstmTcState {
   bool configured;
 };
 
-constexpr int64_t MISC_BYTES = 1024 /*align slack*/ + 8 * (2 * MAX_NS + MAX_MT + 1) + 64;
+constexpr int64_t MISC_BYTES = 1024 /*align slack*/ + 8 * (2 * MAX_NS + MAX_MT + 2) + 64;
 
 // which recurrence kernel the last forward / backward launch used ("v2/cs2", "v1", "steps", ...): exported through
 // lagvae_lstm_variant so that tests and bench.py can assert that the intended kernel ran (no silent fallback)
@@ -1071,7 +1110,11 @@ static bool shape_supported(const lagvae_text_dims& d) {
 size_t lstm_tc_workspace_bytes(const lagvae_text_dims& d, bool use_tc) {
   if (!use_tc) return 0;
   const int64_t Bd = (int64_t)d.B * d.ns, KPb = round_up(4 * d.nh, 64);
-  const int64_t rows = Bd >= 64 ? round_up(Bd, 64) : round_up(Bd, 8);   // v2 tile image: whole row tiles per k-block
+  int64_t rows = round_up(Bd, 64);                                        // v2 tile image: whole row tiles per k-block
+  if (Bd < 64) {
+    rows = 8;
+    while (rows < Bd) rows *= 2;
+  }
   return (size_t)(2 * 2 * rows * KPb * 2 + 1024);   // sized for the backward operand (>= forward's)
 }
 
@@ -1114,6 +1157,11 @@ static int prod_fence_env() {
   return v;
 }
 
+static int bulk_stages_env() {
+  static const int v = [] { const char* e = getenv("LAGVAE_LSTM_BULK_STAGES"); const int n = e ? atoi(e) : 4; return n < 1 ? 1 : (n > 16 ? 16 : n); }();
+  return v;
+}
+
 // ---- v2 (cluster K-split) geometry / launch ---------------------------------------------------------------
 template <bool FWD, int CS_>
 static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) {
@@ -1126,7 +1174,11 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
   const int m_tiles = (int)cdiv(Bd, 64);
   if (m_tiles * C::NALL > 512) return false;
   const int KBS = K / 64 / C::CS;
-  const int rows_alloc = Bd >= 64 ? 64 : (int)round_up(Bd, 8);
+  int rows_alloc = 64;                                   // rows of one operand part of a stage: a power of two (8..64), so that
+  if (Bd < 64) {                                         // a stage is 1, 2, 4 or 8 quarters of 2 KB for the operand copy
+    rows_alloc = 8;
+    while (rows_alloc < Bd) rows_alloc *= 2;
+  }
   const int64_t stage = 2 * (int64_t)rows_alloc * 128;
   const int64_t wbytes = (int64_t)KBS * C::WT;
   const bool stack = m_tiles == 1 && 2 * rows_alloc <= 64;
@@ -1135,6 +1187,9 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
   n = std::min<int64_t>(n, MAX_NS);
   n = std::min<int64_t>(n, std::max(KBS * m_tiles, 2));
   if (n < 2) return false;
+  // the loaders keep a group of stages in registers (16 chunks of 16 B per thread = floor(16 / (stage / 2 KB)) stages) and
+  // store it before arriving on any of its barriers: the ring must hold a whole group
+
   a->part_bytes = rows_alloc * 128;
   a->NS = (int)n;
   a->KP = K;
@@ -1235,6 +1290,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
     LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
   }
   a.prod_fence = prod_fence_env();
+  a.bulk_stages = bulk_stages_env();
   a.dbg = (g_dbg && g_dbg_words >= (size_t)Tn * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
   a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
@@ -1288,6 +1344,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
     LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");
   }
   a.prod_fence = prod_fence_env();
+  a.bulk_stages = bulk_stages_env();
   a.dbg = (g_dbg && g_dbg_words >= (size_t)(Tn + 1) * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
   a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;

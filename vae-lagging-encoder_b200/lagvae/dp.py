@@ -96,6 +96,96 @@ def accumulated_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor]
     return float(loss_sum), norm
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# b3: the UNMODIFIED driver runs SPMD — every rank executes the same script with the same seeds on the same
+# full batch; `VAE.loss` shards the batch by rank internally and returns the FULL [B] vectors, so `loss.sum().item()`,
+# the break rule (text.py:393-398) and every later batch pick agree on all ranks.  The exchange is in the autograd node:
+#   forward : local rows -> (loss, rec, KL)[lo:hi] ; one all-reduce (sum) of a zero-padded [3, B] tensor = the all-gather
+#   backward: upstream gradients sliced to [lo:hi] -> local backward into a flat bucket -> ONE all-reduce (sum) of the
+#             bucket (decoder part first, on a side stream under the encoder backward when the engine exposes the hook)
+# After it every rank holds the gradient of the global mean: clip_grad_norm_ / SGD run by the driver keep the replicas
+# identical without a parameter broadcast.
+class ShardedTextLoss(torch.autograd.Function):
+    """(loss, rec, KL), each the full [B], for a batch sharded over the ranks of `group`.
+
+    `engine` needs: loss_forward(params, x, eps, kl_weight, drop) -> 3 x [b], generation, loss_backward(params, x, g_loss,
+    g_rec, g_kl, generation=, grads_out=) and (optionally) decoder_offset / enable_decoder_grads_event / wait_decoder_grads —
+    lagvae.TextEngine on the GPU, an oracle stand-in in the gloo CPU test."""
+
+    @staticmethod
+    def forward(ctx, engine, group, x, kl_weight, eps, drop_fn, *params):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B = int(x.shape[0])
+        lo, hi = shard_bounds(B, rank, world)
+        p = [q.detach() for q in params]
+        out = torch.zeros(3, B, dtype=torch.float32, device=x.device)
+        ctx.engine, ctx.group, ctx.p, ctx.span, ctx.B = engine, group, p, (lo, hi), B
+        ctx.x_local = x[lo:hi].contiguous() if hi > lo else None
+        ctx.gen = None
+        if hi > lo:
+            loss, rec, kl = engine.loss_forward(p, ctx.x_local, eps[lo:hi].contiguous(), kl_weight, drop_fn(lo, hi))
+            ctx.gen = engine.generation
+            out[0, lo:hi], out[1, lo:hi], out[2, lo:hi] = loss, rec, kl
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)          # 3*B floats: the all-gather of SURVEY §8 b3
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_rec, g_kl):
+        eng, (lo, hi) = ctx.engine, ctx.span
+        dev = g_loss.device
+        # a fresh bucket per backward: the returned gradients are views of it and may become the parameters' .grad
+        flat = torch.empty(sum(int(q.numel()) for q in ctx.p), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for q in ctx.p:
+            views.append(flat[off:off + q.numel()].view(q.shape))
+            off += q.numel()
+        dec_off = getattr(eng, "decoder_offset", None)
+        side = None
+        if hi > lo:
+            Bl, T = int(ctx.x_local.shape[0]), int(ctx.x_local.shape[1])
+            hook = dec_off is not None and hasattr(eng, "enable_decoder_grads_event") and dev.type == "cuda"
+            if hook:
+                eng.enable_decoder_grads_event(Bl, T, getattr(eng, "last_ns", 1))
+            sl = lambda g: None if g is None else g[lo:hi].contiguous()
+            eng.loss_backward(ctx.p, ctx.x_local, sl(g_loss), sl(g_rec), sl(g_kl), generation=ctx.gen, grads_out=views)
+            if hook:
+                side = _side_stream(dev)
+                eng.wait_decoder_grads(Bl, T, getattr(eng, "last_ns", 1), side)
+        else:
+            flat.zero_()                                                  # empty shard (B < world): contributes zeros
+        if dec_off is None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)
+        elif side is not None:
+            flat.record_stream(side)
+            with torch.cuda.stream(side):
+                dist.all_reduce(flat[dec_off:], op=dist.ReduceOp.SUM, group=ctx.group)
+            dist.all_reduce(flat[:dec_off], op=dist.ReduceOp.SUM, group=ctx.group)
+            torch.cuda.current_stream().wait_stream(side)
+        else:                    # same two buckets in the same order on every rank (an empty-shard rank has no event to wait on)
+            dist.all_reduce(flat[dec_off:], op=dist.ReduceOp.SUM, group=ctx.group)
+            dist.all_reduce(flat[:dec_off], op=dist.ReduceOp.SUM, group=ctx.group)
+        return (None, None, None, None, None, None, *views)
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+def dp_group():
+    """The process group `VAE.loss` shards over: the default group when torch.distributed is initialised with more than
+    one rank and LAGVAE_DP != 0; None otherwise (single-process semantics)."""
+    import os
+    if os.environ.get("LAGVAE_DP", "1") == "0" or not dist.is_available() or not dist.is_initialized():
+        return None
+    return dist.group.WORLD if dist.get_world_size() > 1 else None
+
+
 class EngineBackend:
     """Product back-end: lagvae.TextEngine kernels; flat_grads is the engine's flat gradient workspace."""
 
@@ -105,7 +195,6 @@ class EngineBackend:
         self.decoder_offset = engine.decoder_offset
         self._overlap = overlap
         self._side = None
-        self._hooked = set()
 
     def decoder_grads_stream(self, x_local):
         """Side stream that already waits for the decoder gradients of the backward just enqueued (None = no overlap)."""
@@ -122,9 +211,8 @@ class EngineBackend:
         if self._views is None or self._views[0].data_ptr() != flat_grads.data_ptr():
             self._views = eng.split_grads(flat_grads)
         B = x.shape[0]
-        if self._overlap and (B, x.shape[1]) not in self._hooked:
-            eng.enable_decoder_grads_event(B, x.shape[1], 1)
-            self._hooked.add((B, x.shape[1]))
+        if self._overlap:
+            eng.enable_decoder_grads_event(B, x.shape[1], 1)     # idempotent; the engine re-applies it when plans are re-created
         loss, _, _ = eng.loss_forward(params, x, self.eps_fn(B), self.kl_weight, self.drop_fn())
         gl = torch.full((B,), g_scale, dtype=torch.float32, device=x.device)
         # aggressive loop: decoder weights are not stepped, their gradients only enter the clip norm

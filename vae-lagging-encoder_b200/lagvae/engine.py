@@ -66,6 +66,8 @@ class TextEngine:
         self.counts = [int(torch.Size(s).numel()) for s in self.shapes]
         self._ws = None
         self._plans = {}
+        self._hooked = set()   # (B, T, ns) keys whose plans record the decoder-gradient event: re-applied when plans are re-created
+        self.last_ns = 1
         self.generation = 0  # bumped by every forward; backward must match
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_device_check(), "lagvae_device_check")
@@ -103,6 +105,9 @@ class TextEngine:
             be.check(be.lib().lagvae_text_plan_create(C.byref(d), self.flags, C.c_void_p(self._ws.data_ptr()),
                                                       self._ws.numel(), C.byref(out)), "lagvae_text_plan_create")
         self._plans[key] = out
+        if key in self._hooked:          # the workspace grew and every plan was dropped: restore the event hook
+            with torch.cuda.device(self.device):
+                be.check(be.lib().lagvae_text_decoder_grads_event(out, 1), "lagvae_text_decoder_grads_event")
         return out
 
     # ---- argument marshalling ----------------------------------------------------------------
@@ -160,6 +165,7 @@ class TextEngine:
             z = torch.empty(B, ns, self.nz, dtype=torch.float32, device=self.device)
         dc = drop.to_c()
         self.generation += 1
+        self.last_ns = ns
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_loss_forward(
                 h, C.byref(tp), be.ptr(x), be.ptr(eps), float(kl_weight), C.byref(dc), be.ptr(out[0]),
@@ -249,6 +255,10 @@ class TextEngine:
     def enable_decoder_grads_event(self, B, T, ns=1, enable=True):
         """Data-parallel overlap hook (lagvae.h): loss_backward of the (B, T, ns) plan records an event once the 7 decoder
         gradients are final."""
+        key = (int(B), int(T), int(ns))
+        if enable and key in self._hooked and key in self._plans:
+            return
+        (self._hooked.add if enable else self._hooked.discard)(key)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_decoder_grads_event(self.plan(B, T, ns), 1 if enable else 0),
                      "lagvae_text_decoder_grads_event")

@@ -44,19 +44,24 @@ def _detached(ps):
     return [p.detach() for p in ps]
 
 
-def dropout_spec(dec, B, T, ns, device):
-    """Dropout control for one decoder forward.  train(): in-kernel Philox (default) or, with
+def dropout_spec(dec, B, T, ns, device, row_offset=0, rows_total=None):
+    """Dropout control for one decoder forward on B rows.  train(): in-kernel Philox (default) or, with
     LAGVAE_DROPOUT=torch, explicit Bernoulli keep-masks drawn from torch's generator in the reference's
-    order (dropout_in then dropout_out, dec_lstm.py:81,106).  eval(): identity."""
+    order (dropout_in then dropout_out, dec_lstm.py:81,106).  eval(): identity.
+    Under data parallelism the B rows are the shard [row_offset, row_offset + B) of a batch of rows_total sentences:
+    torch masks are drawn for the whole batch (identical on every rank) and sliced; the Philox stream is keyed per shard
+    ("per-rank Philox streams in fast mode; globally generated + sliced in parity mode")."""
     p_in, p_out = float(dec.dropout_in.p), float(dec.dropout_out.p)
     if not dec.training or (p_in == 0.0 and p_out == 0.0):
         return DropoutSpec()
+    total = B if rows_total is None else int(rows_total)
     if os.environ.get("LAGVAE_DROPOUT", "philox") == "torch":
-        m_in = (torch.rand(B, T - 1, dec.ni, device=device) >= p_in).to(torch.uint8) if p_in > 0 else None
-        m_out = (torch.rand(B * ns, T - 1, dec.nh, device=device) >= p_out).to(torch.uint8) if p_out > 0 else None
+        lo, hi = int(row_offset), int(row_offset) + B
+        m_in = (torch.rand(total, T - 1, dec.ni, device=device) >= p_in).to(torch.uint8)[lo:hi].contiguous() if p_in > 0 else None
+        m_out = (torch.rand(total * ns, T - 1, dec.nh, device=device) >= p_out).to(torch.uint8)[lo * ns:hi * ns].contiguous() if p_out > 0 else None
         return DropoutSpec(1, p_in, p_out, m_in, m_out, 0)
     _CALLS[0] += 1
-    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * 0xD1B54A32D192ED03 + int(row_offset) * 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
     return DropoutSpec(2, p_in, p_out, None, None, seed)
 
 

@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from lagvae import LagvaeError
+from lagvae.dp import ShardedTextLoss, dp_group
 
 from .text import LSTMDecoder, LSTMEncoder, _dec_params, _enc_params, dropout_spec, get_engine
 from .utils import log_sum_exp
@@ -90,8 +91,14 @@ class VAE(nn.Module):
         eng = self._text_engine()
         B, T = x.shape
         eps = torch.empty(B, nsamples, self.nz, dtype=torch.float32, device=x.device).normal_()  # encoder.py:77
-        drop = dropout_spec(self.decoder, B, T, nsamples, x.device)
         params = _enc_params(self.encoder) + _dec_params(self.decoder)
+        group = dp_group()
+        if group is not None:
+            # SPMD data parallelism inside the boundary: every rank was handed the same full batch and
+            # drew the same eps; each computes its row shard and the autograd node exchanges (lagvae/dp.py)
+            drop_fn = lambda lo, hi: dropout_spec(self.decoder, hi - lo, T, nsamples, x.device, row_offset=lo, rows_total=B)
+            return ShardedTextLoss.apply(eng, group, x, float(kl_weight), eps, drop_fn, *params)
+        drop = dropout_spec(self.decoder, B, T, nsamples, x.device)
         return _TextLossFn.apply(eng, x, float(kl_weight), eps, drop, *params)
 
     def nll_iw(self, x, nsamples, ns=100):
