@@ -373,22 +373,25 @@ def run_ours(args, rank, world, local_rank):
         vae.train()
         enc_opt = torch.optim.SGD(vae.encoder.parameters(), lr=1.0, momentum=0)
         dec_opt = torch.optim.SGD(vae.decoder.parameters(), lr=1.0, momentum=0)
-        host_pool = [t.cpu().pin_memory() for t in pool[:16]]
-        xdev = torch.empty(B, T, dtype=torch.int64, device=dev)
+        # N > 1: the SPMD contract of SURVEY §8 b3 — every rank runs the SAME statements on the SAME global batch
+        # (32 sentences per GPU: rows [32 r, 32 r + 32) are rank r's shard); `VAE.loss` shards it by rank internally, returns
+        # the full vectors and all-reduces the flat gradient bucket in its backward (lagvae_allreduce_bucket)
+        if world == 1:
+            host_pool = [t.cpu().pin_memory() for t in pool[:16]]
+        else:
+            host_pool = [torch.cat([O.make_token_batch(B, T, V, seed=1234 + 1000 * r + i) for r in range(world)]).pin_memory()
+                         for i in range(16)]
+        xdev = torch.empty(B * world, T, dtype=torch.int64, device=dev)
         allp = list(vae.parameters())
 
         def step_api(i):
             xdev.copy_(host_pool[picks[i] % 16], non_blocking=True)               # H2D of this step's input
             enc_opt.zero_grad()
             dec_opt.zero_grad()
-            loss, loss_rc, loss_kl = vae.loss(xdev, KL_WEIGHT, nsamples=1)        # text.py:379
+            loss, loss_rc, loss_kl = vae.loss(xdev, KL_WEIGHT, nsamples=1)        # text.py:379 (sharded over the ranks inside)
             s = loss.sum().item()                                                 # text.py:381 (D2H sync)
             loss = loss.mean(dim=-1)
-            loss.backward()                                                       # text.py:384
-            if world > 1:
-                for q in allp:
-                    q.grad.div_(world)
-                    dist.all_reduce(q.grad)
+            loss.backward()                                                       # text.py:384 (+ the bucket all-reduce)
             torch.nn.utils.clip_grad_norm_(allp, 5.0)                             # text.py:385
             enc_opt.step()                                                        # text.py:387
             return s
@@ -406,9 +409,11 @@ def run_ours(args, rank, world, local_rank):
         ems = torch.tensor([f0.elapsed_time(f1)], device=dev)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_e2e / (float(ems) / 1e3), "unit": "steps/s", "h2d_bytes_per_step": B * T * 8,
+        e2e = {"value": world * n_e2e / (float(ems) / 1e3), "unit": "steps/s", "h2d_bytes_per_step": B * world * T * 8,
                "d2h_bytes_per_step": 4, "steps": n_e2e,
-               "api": "modules.VAE.loss -> backward -> clip_grad_norm_ -> SGD.step (text.py:373-387 sequence)"}
+               "api": "modules.VAE.loss -> backward -> clip_grad_norm_ -> SGD.step (text.py:373-387 sequence)" +
+                      ("; SPMD: every rank is handed the global batch of %d sentences, VAE.loss shards it by rank and all-reduces "
+                       "the flat gradient bucket (lagvae_allreduce_bucket) in its backward" % (B * world) if world > 1 else "")}
         del vae, enc_opt, dec_opt
         torch.cuda.empty_cache()
 

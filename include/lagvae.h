@@ -126,6 +126,12 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* plan, const lagvae_text_para
                                   const int64_t* x, const float* z, const lagvae_dropout* drop,
                                   float* out_rec_rows, void* stream);
 
+/* Decoder only: LSTMDecoder.decode — dec_lstm.py:66-111.  `input` int64 [B, T-1] row-major (the plan's T minus one: the
+ * decoder consumes T-1 tokens), z fp32 [B*ns, nz]; out_logits fp32 [B*ns, T-1, V] row-major, the tensor the reference returns
+ * (vocabulary projection of every position, dec_lstm.py:109).  Forward only. */
+int lagvae_text_decode_logits(lagvae_text_plan* plan, const lagvae_text_params* params, const int64_t* input,
+                              const float* z, const lagvae_dropout* drop, float* out_logits, void* stream);
+
 /* clip_grad_norm_(all params, max_norm) + SGD(momentum 0) on the first `n_update` tensors —
  * text.py:385 + text.py:387 (optim.SGD text.py:325).  segs: `n_seg` (ptr,count) pairs describing
  * the gradient tensors; params/grads pair up by index.  out_norm (device fp32[1]) receives the
@@ -135,6 +141,37 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* plan, const lagvae_text_para
 int lagvae_clip_sgd_step(float* const* h_params, float* const* h_grads, const int64_t* h_counts,
                          int n_seg, int n_update, float max_norm, float lr, int scale_all_grads,
                          float* out_norm, void* scratch, void* stream);
+
+/* clip_grad_norm_(all params, max_norm) + torch.optim.Adam step (amsgrad False, no weight decay) on the first
+ * `n_update` tensors — image.py:312 + image.py:314 (optim.Adam(lr=0.001) image.py:267; toy.py:289-290).  The image model
+ * has 248 parameter tensors, so the (param, grad, exp_avg, exp_avg_sq, count) tuples live in a device-resident table built
+ * once: `lagvae_adam_table_create` uploads it into caller-owned device memory (>= lagvae_adam_table_bytes, 256-B aligned;
+ * synchronous, call it outside graph capture); `lagvae_clip_adam_step` is then three launches and capturable: Adam's step
+ * count (bias correction) lives on the device, starts at `initial_step` and is incremented by every call.  exp_avg /
+ * exp_avg_sq are caller-owned fp32 tensors (the optimizer state, zero before the first step).  scale_all_grads as in
+ * lagvae_clip_sgd_step.  out_norm: device fp32[1] or NULL. */
+typedef struct lagvae_adam_table lagvae_adam_table;
+size_t lagvae_adam_table_bytes(const int64_t* h_counts, int n_seg);
+int lagvae_adam_table_create(float* const* h_params, float* const* h_grads, float* const* h_exp_avg,
+                             float* const* h_exp_avg_sq, const int64_t* h_counts, int n_seg, int n_update,
+                             int initial_step, void* device_mem, size_t device_bytes, void* stream,
+                             lagvae_adam_table** out);
+void lagvae_adam_table_destroy(lagvae_adam_table* table);
+int lagvae_clip_adam_step(lagvae_adam_table* table, float max_norm, float lr, float beta1, float beta2, float eps,
+                          int scale_all_grads, float* out_norm, void* stream);
+
+/* The data-path collective of the batch-sharded inner step (the single-process reference has no
+ * counterpart: its loop body is text.py:371-391): ONE sum all-reduce of the flat fp32 gradient bucket per inner step over
+ * NCCL / NVLink, the communicator owned by the library.  NCCL is bound at run time: `lagvae_comm_load` dlopen()s the
+ * libnccl.so.2 the host side points it to (torch's bundled copy), `lagvae_comm_unique_id` (rank 0) fills a 128-byte id that
+ * the caller distributes to the other ranks out of band, `lagvae_comm_init` is collective over the `world` ranks (one
+ * process per GPU, current device).  `lagvae_allreduce_bucket` enqueues the all-reduce of bucket[0, count) on `stream`. */
+typedef struct lagvae_comm lagvae_comm;
+int lagvae_comm_load(const char* libnccl_path);
+int lagvae_comm_unique_id(void* out_128_bytes);
+int lagvae_comm_init(const void* uid_128_bytes, int rank, int world, lagvae_comm** out);
+int lagvae_allreduce_bucket(lagvae_comm* comm, float* bucket, int64_t count, void* stream);
+void lagvae_comm_destroy(lagvae_comm* comm);
 
 /* MI estimate from posterior stats — encoder.py:111-145 (+utils.py:3-16).  mu/logvar [B,nz], eps
  * [B,nz] (the draw of encoder.py:128).  out_mi: device fp32[1]. */
@@ -150,6 +187,15 @@ int lagvae_text_inner_step(lagvae_text_plan* plan, const lagvae_text_params* par
                            const int64_t* x, const float* eps, float kl_weight,
                            const lagvae_dropout* drop, float max_norm, float lr, float* grad_ws,
                            float* out_loss, float* out_scalars, void* stream);
+
+/* The decoder-update step that closes every outer iteration — text.py:407-424: zero-grad, loss fwd, backward of mean(loss),
+ * clip(max_norm) over all 13 grads, then `dec_optimizer.step()` and, once the aggressive phase is over (`update_encoder`
+ * != 0, text.py:421-422), `enc_optimizer.step()` too — SGD(lr, momentum 0) both (text.py:325-326).  Same buffers and
+ * out_scalars as lagvae_text_inner_step; all gradients are computed at full (3-pass) precision here. */
+int lagvae_text_outer_step(lagvae_text_plan* plan, const lagvae_text_params* params, const int64_t* x,
+                           const float* eps, float kl_weight, const lagvae_dropout* drop, float max_norm,
+                           float lr, int update_encoder, float* grad_ws, float* out_loss, float* out_scalars,
+                           void* stream);
 
 /* Data-parallel overlap hook (no counterpart in the single-process reference).  The decoder
  * gradients (the last 7 tensors of vae.parameters(), 70% of the bucket) are final before the encoder LSTM

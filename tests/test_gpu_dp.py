@@ -117,3 +117,48 @@ def test_two_gpu_sharded_vae_loss_matches_single_gpu(shape):
         assert np.array_equal(a, b)                       # replicas stay bit-identical without a parameter broadcast
     for a, b in zip(res[0]["dp"][4], res[1]["dp"][4]):
         assert np.array_equal(a, b)
+
+
+def _comm_worker(rank, world, port, out_q):
+    for p_ in (os.path.join(ROOT, "vae-lagging-encoder_b200"),):
+        sys.path.insert(0, p_)
+    import torch.distributed as dist
+    import lagvae
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    comm = lagvae.BucketComm()
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    flat = torch.randn(1 << 20, generator=g, device=dev)
+    want = flat.clone()
+    dist.all_reduce(want)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    comm.all_reduce(flat[: 1 << 19])                       # current stream
+    comm.all_reduce(flat[1 << 19:], side)                  # explicit side stream (the decoder-bucket overlap path)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    out_q.put((rank, bool(torch.equal(flat, want)) or float((flat - want).abs().max())))
+    comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_library_owned_nccl_bucket_allreduce_matches_torch():
+    """lagvae_allreduce_bucket (communicator created by liblagvae.so through dlopen'd NCCL) == torch.distributed.all_reduce."""
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world, port = 2, 35000 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    for rank, ok in res.items():
+        assert ok is True or ok < 1e-6, (rank, ok)         # NCCL's ring order may differ in the last bit between communicators

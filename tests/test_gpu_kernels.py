@@ -210,3 +210,33 @@ def test_lstm_persistent_tcgen05_matches_step_tier(nh, Bd, Tn, init, dropout):
         err = float((a - b).abs().max() / (b.abs().max() + 1e-20))
         assert err < 2e-4, "%s: rel err %.3e" % (n, err)
     assert float(res[0][2].abs().max()) > 0.05   # the comparison is not vacuous
+
+
+@pytest.mark.parametrize("scale", [0.05, 40.0], ids=["below-clip", "above-clip"])
+def test_clip_adam_matches_torch(scale):
+    """lagvae_clip_adam_step (image.py:312-314: clip_grad_norm_ over ALL parameters, Adam on the encoder's) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.Adam over several steps; more tensors than fit a kernel-argument table."""
+    import lagvae
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(64, 3, 3, 3), (64,), (64,), (5000,), (33, 7), (1,)] * 6 + [(20000,), (17,)]
+    n_update = 20
+    ps = [torch.randn(*s, generator=g, device="cuda") for s in shapes]
+    ref_p = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.Adam(ref_p[:n_update], lr=1e-3)
+    grads = [torch.zeros_like(p) for p in ps]
+    ca = lagvae.ClipAdam(ps, grads, n_update, lr=1e-3, max_norm=5.0)
+    for it in range(4):
+        new = [scale * torch.randn(*s, generator=g, device="cuda") for s in shapes]
+        for gr, nw, rp in zip(grads, new, ref_p):
+            gr.copy_(nw)
+            rp.grad = nw.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref_p, 5.0)
+        opt.step()
+        norm = ca.step()
+        assert abs(float(norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+        for p, rp, gr in zip(ps, ref_p, grads):
+            assert float((gr - rp.grad).abs().max()) <= 1e-6 * max(1.0, float(rp.grad.abs().max()))
+            # Adam's update is lr * m / (sqrt(v) + eps): a relative rounding difference in sqrt/div moves p by ~lr * 1e-6
+            assert float((p - rp.detach()).abs().max()) <= 2e-6 * max(1.0, float(rp.detach().abs().max())), it
+    for p, rp in zip(ps[n_update:], ref_p[n_update:]):
+        assert torch.equal(p, rp.detach())            # tensors beyond n_update are never stepped

@@ -387,3 +387,88 @@ def test_fused_inner_step_full_shape_loss_and_norm(golden):
     grads = eng.split_grads(gw)
     n_pred = float(grads[12].double().norm())
     assert abs(n_pred - float(g["gnorm.decoder.pred_linear.weight"])) <= 2e-3 * float(g["gnorm.decoder.pred_linear.weight"])
+
+
+@pytest.mark.parametrize("name", ["aligned_ns3_eval", "toy_eval"])
+def test_decoder_decode_returns_the_reference_logits(golden, name):
+    """LSTMDecoder.decode(input, z) (dec_lstm.py:66-111) through the drop-in module: logits [B*ns, T-1, V] against the oracle's
+    decoder, and consistent with reconstruct_error (CE of those logits against the shifted tokens, dec_lstm.py:113-148)."""
+    g = golden(name)
+    c = case_inputs(g)
+    p = case_params(g)
+    vae = _build_modules(c, p).eval()
+    x = c["x"].cuda()
+    mu, lv = O.encoder_forward(p, c["x"])
+    z = O.reparameterize(mu, lv, c["eps"])                                   # [B, ns, nz]
+    with torch.no_grad():
+        logits = vae.decoder.decode(x[:, :-1], z.cuda().contiguous())
+    B, ns, T, V = c["B"], c["ns"], c["T"], c["V"]
+    assert logits.shape == (B * ns, T - 1, V)
+    tgt = x[:, 1:].unsqueeze(1).expand(B, ns, T - 1).reshape(-1)
+    ce = torch.nn.functional.cross_entropy(logits.reshape(-1, V), tgt, reduction="none").view(B, ns, T - 1).sum(-1)
+    want = O.decoder_reconstruct_error(p, c["x"], z)
+    assert_close(ce, want, OUT_TOL, "CE of decode() logits vs oracle reconstruct_error")
+    got = vae.decoder.reconstruct_error(x, z.cuda().contiguous())
+    assert_close(got, want, OUT_TOL, "reconstruct_error")
+
+
+@pytest.mark.parametrize("update_encoder", [False, True], ids=["aggressive", "vanilla"])
+@pytest.mark.parametrize("name", ["toy_eval", "aligned_ns3_eval"])
+def test_decoder_update_step_matches_oracle(golden, name, update_encoder):
+    """the step that closes every outer iteration (text.py:407-424) — loss, backward, clip over all 13
+    gradients, dec_optimizer.step() and (after the aggressive phase) enc_optimizer.step() — (a) through the drop-in modules
+    with the stock torch optimisers, (b) through the fused lagvae_text_outer_step; both against the oracle's gradients."""
+    g = golden(name)
+    c = case_inputs(g)
+    if c["ns"] != 1:
+        c = dict(c, ns=1, eps=c["eps"][:, :1].contiguous())
+    p = case_params(g)
+    r = O.inner_step({k: v.clone() for k, v in p.items()}, c["x"], c["klw"], c["eps"], update=False, max_norm=0.5)
+    coef = r["coef"]
+    assert coef < 1.0
+    upd = set(O.DEC_KEYS) | (set(O.ENC_KEYS) if update_encoder else set())
+    want = {k: (p[k] - coef * r["grads"][k]) if k in upd else p[k] for k in O.ALL_KEYS}
+    # (b) fused step
+    eng = _engine(c, False)
+    params = _plist(p)
+    gw = eng.grad_workspace()
+    out_loss, sc = torch.empty(c["B"], device="cuda"), torch.empty(4, device="cuda")
+    eng.outer_step(params, c["x"].cuda(), c["eps"].cuda(), c["klw"], None, gw, out_loss, sc, update_encoder, max_norm=0.5)
+    assert_close(out_loss, r["loss"], OUT_TOL, "loss")
+    assert abs(float(sc[3]) - r["grad_norm"]) <= 1e-3 * r["grad_norm"]
+    for q, k in zip(params, O.ALL_KEYS):
+        if k in upd:
+            d_want, d_got = want[k] - p[k], q.cpu() - p[k]
+            assert_close(d_got, d_want, GRAD_TOL, "update of " + k, floor=1e-9)
+        else:
+            assert torch.equal(q.cpu(), p[k]), k
+    # (a) module API + torch optimisers, driver statements
+    vae = _build_modules(c, p).eval()
+    enc_opt = torch.optim.SGD(vae.encoder.parameters(), lr=1.0, momentum=0)
+    dec_opt = torch.optim.SGD(vae.decoder.parameters(), lr=1.0, momentum=0)
+    import modules
+    eps_dev = c["eps"].cuda()
+    orig = modules.vae.torch.empty
+
+    class _Eps:          # replay the oracle's eps for the single normal_() draw of VAE.loss (encoder.py:77)
+        def __call__(self, *a, **k):
+            t = orig(*a, **k)
+            if tuple(t.shape) == tuple(eps_dev.shape):
+                t.normal_ = lambda: t.copy_(eps_dev)
+            return t
+    enc_opt.zero_grad()
+    dec_opt.zero_grad()
+    torch.manual_seed(0)
+    loss, loss_rc, loss_kl = vae.loss(c["x"].cuda(), c["klw"], nsamples=1)     # text.py:411 (own eps draw)
+    loss.mean(dim=-1).backward()                                                # text.py:413-415
+    torch.nn.utils.clip_grad_norm_(vae.parameters(), 0.5)                       # text.py:416
+    before = {k: q.detach().clone() for k, q in vae.named_parameters()}
+    grads = {k: q.grad.detach().clone() for k, q in vae.named_parameters()}
+    if update_encoder:
+        enc_opt.step()                                                          # text.py:421-422
+    dec_opt.step()                                                              # text.py:424
+    for k, q in vae.named_parameters():
+        if k in upd:
+            assert torch.allclose(q.detach(), before[k] - grads[k], rtol=0, atol=1e-7 * float(before[k].abs().max()) + 1e-12), k
+        else:
+            assert torch.equal(q.detach(), before[k]), k

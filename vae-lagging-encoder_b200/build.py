@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(HERE, "lagvae")
 BUILD_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "liblagvae.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "lstm_tc.cu", "text_plan.cu", "image_kernels.cu", "conv_tc.cu", "image_fused.cu", "image_plan.cu"]
+SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "lstm_tc.cu", "text_plan.cu", "image_kernels.cu", "conv_tc.cu", "image_fused.cu", "image_plan.cu", "comm_optim.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -430,6 +430,20 @@ __global__ void k_time_sum(const float* __restrict__ src, int Tn, int Bd, int nc
     out[i] = (a0 + a1) + (a2 + a3);
   }
 }
+// time-major logits [Tn*Bd, ld] -> batch-major [Bd, Tn, V] (the layout LSTMDecoder.decode returns, dec_lstm.py:109-111)
+__global__ void __launch_bounds__(256) k_logits_batch_major(const float* __restrict__ src, int64_t ld, int V, int Tn, int Bd,
+                                                            float* __restrict__ out) {
+  const int64_t row = blockIdx.x;                 // output row = bd * Tn + t
+  const int bd = (int)(row / Tn), t = (int)(row - (int64_t)bd * Tn);
+  const float* s = src + ((int64_t)t * Bd + bd) * ld;
+  float* o = out + row * V;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) o[v] = s[v];
+}
+int logits_batch_major(const float* src, int64_t ld, int V, int Tn, int Bd, float* out, cudaStream_t st) {
+  k_logits_batch_major<<<(unsigned)((int64_t)Tn * Bd), 256, 0, st>>>(src, ld, V, Tn, Bd, out);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
 int time_sum(const float* src, int Tn, int Bd, int ncol, float* out, cudaStream_t st) {
   const int64_t n = (int64_t)Bd * ncol;
   k_time_sum<<<(int)std::min<int64_t>(cdiv(n, 128), 148 * 16), 128, 0, st>>>(src, Tn, Bd, ncol, out);

@@ -319,14 +319,17 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
 
 
 // decoder forward up to per-token CE (dec_lstm.py:66-148).  z: device [Bd, nz].
+// x_ld: row stride of the token tensor (d.T for the [B,T] training batches, T-1 for LSTMDecoder.decode's `input`);
+// with_ce = false stops after the vocabulary projection (targets are not read).
 int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, const float* z,
-                    const lagvae_dropout& dr, cudaStream_t st) {
+                    const lagvae_dropout& dr, cudaStream_t st, int64_t x_ld = -1, bool with_ce = true) {
   const lagvae_text_dims& d = P->d;
   const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td;
   int status = LAGVAE_OK;
   // ---- decoder: dec_lstm.py:66-111
   const DropSpec din = spec_in(dr), dout = spec_out(dr);
-  LV_TRY(embed_gather(x, d.T, 0, B, ns, Td, w->p[D_EMB], ni, din, P->xd, st));                // :80-81 (+:87-91)
+  if (x_ld < 0) x_ld = d.T;
+  LV_TRY(embed_gather(x, x_ld, 0, B, ns, Td, w->p[D_EMB], ni, din, P->xd, st));               // :80-81 (+:87-91)
   LV_TRY(vec_add(w->p[D_BIH], w->p[D_BHH], P->bsum_d, 4 * nh, st));
   // z enters every step through the last nz input columns (:84,97): time-invariant row bias
   LV_TRY(gemm_f32(z, nz, 1, w->p[D_WIH] + ni, ni + nz, 1, P->zb, 4 * nh, Bd, 4 * nh, nz, 1.f, 0.f,
@@ -350,7 +353,7 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
   LV_TRY(status);
   LV_TRY(mm(P, sh, false, swp, false, P->logits, P->ldl, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
-  LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
+  if (with_ce) LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
   return LAGVAE_OK;
 }
 
@@ -535,6 +538,20 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* P, const lagvae_text_params*
   return LAGVAE_OK;
 }
 
+int lagvae_text_decode_logits(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* input,
+                              const float* z, const lagvae_dropout* drop, float* out_logits, void* stream) {
+  LV_CHECK_ARG(P && w && input && z && out_logits, "decode_logits: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  lagvae_dropout dr{};
+  if (drop) dr = *drop;
+  LV_CHECK_ARG(dr.mode >= 0 && dr.mode <= 2 && dr.p_in < 1.f && dr.p_out < 1.f, "decode_logits: bad dropout");
+  P->arena_off = 0;
+  P->have_forward = false;
+  LV_TRY(decoder_forward(P, w, input, z, dr, st, P->Td, false));
+  LV_TRY(logits_batch_major(P->logits, P->ldl, P->d.V, P->Td, P->Bd, out_logits, st));
+  return LAGVAE_OK;
+}
+
 int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
                               const float* g_loss, const float* g_rec, const float* g_kl,
                               const lagvae_text_params* gr, uint32_t flags, void* stream) {
@@ -704,10 +721,9 @@ int lagvae_mi_estimate(const float* mu, const float* logvar, const float* eps, i
   return mi_estimate(mu, logvar, eps, B, nz, out_mi, (cudaStream_t)stream);
 }
 
-int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
-                           const float* eps, float kl_weight, const lagvae_dropout* drop, float max_norm,
-                           float lr, float* grad_ws, float* out_loss, float* out_scalars, void* stream) {
-  LV_CHECK_ARG(P && w && x && eps && grad_ws && out_loss && out_scalars, "inner_step: null argument");
+static int text_step(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, const float* eps, float kl_weight,
+                     const lagvae_dropout* drop, float max_norm, float lr, bool upd_enc, bool upd_dec, float* grad_ws,
+                     float* out_loss, float* out_scalars, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const lagvae_text_dims& d = P->d;
   const int64_t V = d.V, ni = d.ni, nh = d.nh, nz = d.nz;
@@ -720,18 +736,50 @@ int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, con
     g.p[i] = grad_ws + off;
     off += counts[i];
   }
-  // text.py:379 loss; :381 Σloss; :382 mean(dim=-1) -> upstream 1/B
+  // text.py:379 / :411 loss; :381 Σloss; :382 / :413 mean(dim=-1) -> upstream 1/B
   LV_TRY(lagvae_text_loss_forward(P, w, x, eps, kl_weight, drop, out_loss, P->dml /*rec tmp*/, P->dh_last /*kl tmp*/,
                                   nullptr, nullptr, nullptr, stream));
   LV_CUDA(cudaMemcpyAsync(out_scalars, P->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   LV_TRY(fill(P->dc0t, 1.f / (float)d.B, d.B, st));
-  // decoder WEIGHT gradients are never applied in this loop (text.py:387 steps the encoder only); they enter
-  // the update through the clip norm alone (text.py:385), for which one bf16 pass is ample (norm error ~1e-5)
-  LV_TRY(lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g, LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY, stream));
-  // text.py:385 clip over all 13 grads; :387 encoder-only SGD step
-  LV_TRY(clip_sgd_step(w->p, g.p, counts, LAGVAE_TEXT_NPARAM, 6, max_norm, lr, 0, out_scalars + 3,
-                       P->clip_scratch, st));
+  // Decoder WEIGHT gradients that are not applied (aggressive inner loop: text.py:387 steps the encoder only) enter the
+  // update through the clip norm alone (text.py:385), for which one bf16 pass is ample (norm error ~1e-5); when the
+  // decoder is stepped (text.py:424) they are computed at full 3-pass precision.
+  LV_TRY(lagvae_text_loss_backward(P, w, x, P->dc0t, nullptr, nullptr, &g,
+                                   upd_dec ? LAGVAE_BWD_DEFAULT : LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY, stream));
+  // text.py:385 / :414 clip over all 13 grads; then SGD on the selected halves (updated tensors first in the segment list)
+  float* pp[LAGVAE_TEXT_NPARAM];
+  float* gg[LAGVAE_TEXT_NPARAM];
+  int64_t cc[LAGVAE_TEXT_NPARAM];
+  int n = 0, n_upd = 0;
+  auto push = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i, ++n) {
+      pp[n] = const_cast<float*>(w->p[i]);
+      gg[n] = g.p[i];
+      cc[n] = counts[i];
+    }
+  };
+  if (upd_enc) { push(0, 6); n_upd = n; }
+  if (upd_dec) { push(6, LAGVAE_TEXT_NPARAM); n_upd = n; }
+  if (!upd_enc) push(0, 6);
+  if (!upd_dec) push(6, LAGVAE_TEXT_NPARAM);
+  LV_TRY(clip_sgd_step(pp, gg, cc, LAGVAE_TEXT_NPARAM, n_upd, max_norm, lr, 0, out_scalars + 3, P->clip_scratch, st));
   return LAGVAE_OK;
+}
+
+int lagvae_text_inner_step(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                           const float* eps, float kl_weight, const lagvae_dropout* drop, float max_norm,
+                           float lr, float* grad_ws, float* out_loss, float* out_scalars, void* stream) {
+  LV_CHECK_ARG(P && w && x && eps && grad_ws && out_loss && out_scalars, "inner_step: null argument");
+  return text_step(P, w, x, eps, kl_weight, drop, max_norm, lr, true, false, grad_ws, out_loss, out_scalars, stream);
+}
+
+int lagvae_text_outer_step(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x,
+                           const float* eps, float kl_weight, const lagvae_dropout* drop, float max_norm,
+                           float lr, int update_encoder, float* grad_ws, float* out_loss, float* out_scalars,
+                           void* stream) {
+  LV_CHECK_ARG(P && w && x && eps && grad_ws && out_loss && out_scalars, "outer_step: null argument");
+  return text_step(P, w, x, eps, kl_weight, drop, max_norm, lr, update_encoder != 0, true, grad_ws, out_loss, out_scalars,
+                   stream);
 }
 
 size_t lagvae_lstm_workspace_bytes(int nh, int Bd) {

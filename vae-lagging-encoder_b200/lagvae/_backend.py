@@ -64,11 +64,24 @@ PROTOTYPES = {
                                        C.POINTER(TextParams), _u32, _vp]),
     "lagvae_text_encode_stats": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _vp, _vp]),
     "lagvae_text_reconstruct_error": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, C.POINTER(Dropout), _vp, _vp]),
+    "lagvae_text_decode_logits": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, C.POINTER(Dropout), _vp, _vp]),
     "lagvae_clip_sgd_step": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _f, _f, _i,
                                   _vp, _vp, _vp]),
     "lagvae_mi_estimate": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "lagvae_adam_table_bytes": (_sz, [C.POINTER(_i64), _i]),
+    "lagvae_adam_table_create": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _i,
+                                      _vp, _sz, _vp, C.POINTER(_vp)]),
+    "lagvae_adam_table_destroy": (None, [_vp]),
+    "lagvae_clip_adam_step": (_i, [_vp, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "lagvae_comm_load": (_i, [C.c_char_p]),
+    "lagvae_comm_unique_id": (_i, [_vp]),
+    "lagvae_comm_init": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "lagvae_allreduce_bucket": (_i, [_vp, _vp, _i64, _vp]),
+    "lagvae_comm_destroy": (None, [_vp]),
     "lagvae_text_param_count": (_i64, [C.POINTER(TextDims)]),
     "lagvae_text_inner_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f,
+                                    _vp, _vp, _vp, _vp]),
+    "lagvae_text_outer_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f, _i,
                                     _vp, _vp, _vp, _vp]),
     "lagvae_text_decoder_grads_event": (_i, [_vp, _i]),
     "lagvae_text_wait_decoder_grads": (_i, [_vp, _vp]),

@@ -153,21 +153,42 @@ class ShardedTextLoss(torch.autograd.Function):
                 eng.wait_decoder_grads(Bl, T, getattr(eng, "last_ns", 1), side)
         else:
             flat.zero_()                                                  # empty shard (B < world): contributes zeros
+        # the collective itself: lagvae_allreduce_bucket (NCCL communicator owned by liblagvae.so) on CUDA, torch.distributed
+        # otherwise (gloo in the CPU tests, or LAGVAE_DP_COMM=torch)
+        comm = _bucket_comm(ctx.group, dev)
+        reduce = (lambda t, st=None: comm.all_reduce(t, st)) if comm is not None else \
+                 (lambda t, st=None: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=ctx.group))
         if dec_off is None:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)
+            reduce(flat)
         elif side is not None:
             flat.record_stream(side)
             with torch.cuda.stream(side):
-                dist.all_reduce(flat[dec_off:], op=dist.ReduceOp.SUM, group=ctx.group)
-            dist.all_reduce(flat[:dec_off], op=dist.ReduceOp.SUM, group=ctx.group)
+                reduce(flat[dec_off:], side)
+            reduce(flat[:dec_off])
             torch.cuda.current_stream().wait_stream(side)
         else:                    # same two buckets in the same order on every rank (an empty-shard rank has no event to wait on)
-            dist.all_reduce(flat[dec_off:], op=dist.ReduceOp.SUM, group=ctx.group)
-            dist.all_reduce(flat[:dec_off], op=dist.ReduceOp.SUM, group=ctx.group)
+            reduce(flat[dec_off:])
+            reduce(flat[:dec_off])
         return (None, None, None, None, None, None, *views)
 
 
 _SIDE = {}
+_COMMS = {}
+
+
+def _bucket_comm(group, dev):
+    """lagvae.BucketComm for `group` (created on first use; collective), or None when the bucket is not on a CUDA device or
+    LAGVAE_DP_COMM=torch asks for torch.distributed's all_reduce."""
+    import os
+    if dev.type != "cuda" or os.environ.get("LAGVAE_DP_COMM", "lagvae") == "torch":
+        return None
+    key = id(group)
+    if key not in _COMMS:
+        from .optim import BucketComm
+        with torch.cuda.device(dev):
+            _COMMS[key] = BucketComm(group)
+    return _COMMS[key]
+
 
 
 def _side_stream(dev):

@@ -224,6 +224,23 @@ class TextEngine:
                      "lagvae_text_reconstruct_error")
         return out
 
+    def decode_logits(self, params, src, z, drop=None):
+        """LSTMDecoder.decode (dec_lstm.py:66-111): src int64 [B, T'] (decoder input tokens), z [B, ns, nz] ->
+        logits [B*ns, T', V].  Forward only."""
+        src = self._x(src)
+        B, Td = src.shape
+        ns = int(z.shape[1])
+        z = self._f32(z, (B, ns, self.nz), "z")
+        drop = self._check_drop(drop, B, Td + 1, ns)
+        tp = self._params(params)
+        out = torch.empty(B * ns, Td, self.V, dtype=torch.float32, device=self.device)
+        dc = drop.to_c()
+        self.generation += 1
+        with torch.cuda.device(self.device):
+            be.check(be.lib().lagvae_text_decode_logits(self.plan(B, Td + 1, ns), C.byref(tp), be.ptr(src), be.ptr(z),
+                                                        C.byref(dc), be.ptr(out), _stream()), "lagvae_text_decode_logits")
+        return out
+
     def mi(self, mu, logvar, eps):
         B, nz = mu.shape
         mu, logvar = self._f32(mu, (B, nz), "mu"), self._f32(logvar, (B, nz), "logvar")
@@ -294,4 +311,21 @@ class TextEngine:
                                                      float(kl_weight), C.byref(dc), float(max_norm), float(lr),
                                                      be.ptr(grad_ws), be.ptr(out_loss), be.ptr(out_scalars),
                                                      _stream()), "lagvae_text_inner_step")
+        self._last = (x, eps, drop)
+
+    def outer_step(self, params, x, eps, kl_weight, drop, grad_ws, out_loss, out_scalars, update_encoder, max_norm=5.0, lr=1.0):
+        """The fused decoder-update step of text.py:407-424 (device side): decoder SGD step, plus the encoder's when
+        `update_encoder` (aggressive phase over).  Same buffers as inner_step."""
+        x = self._x(x)
+        B, T = x.shape
+        ns = int(eps.shape[1])
+        drop = self._check_drop(drop, B, T, ns)
+        tp = self._params(params)
+        dc = drop.to_c()
+        self.generation += 1
+        with torch.cuda.device(self.device):
+            be.check(be.lib().lagvae_text_outer_step(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(eps),
+                                                     float(kl_weight), C.byref(dc), float(max_norm), float(lr),
+                                                     1 if update_encoder else 0, be.ptr(grad_ws), be.ptr(out_loss),
+                                                     be.ptr(out_scalars), _stream()), "lagvae_text_outer_step")
         self._last = (x, eps, drop)

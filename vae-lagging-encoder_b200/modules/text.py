@@ -191,8 +191,12 @@ class LSTMDecoder(DecoderBase):
         return -self.reconstruct_error(x, z)                      # dec_lstm.py:151-161
 
     def decode(self, input, z):
-        raise NotImplementedError("materialised training logits are never exposed by the fused decoder; "
-                                  "use reconstruct_error / log_probability (generation: greedy/sample/beam_search_decode)")
+        """Logits of every position, [B*ns, T', V] (dec_lstm.py:66-111): input int64 [B, T'], z [B, ns, nz].
+        Forward-only entry (the training path never materialises this tensor on the host side; gradients flow through
+        VAE.loss)."""
+        B, Td = input.shape
+        drop = dropout_spec(self, B, Td + 1, z.shape[1], input.device)
+        return self._engine().decode_logits([None] * 6 + _detached(_dec_params(self)), input, z.detach(), drop)
 
     # ---- generation (dec_lstm.py:163-367; SURVEY §8 f4): host-driven token loops, exactly like the reference, over ONE
     #      decoder time step computed by liblagvae.so kernels (input projection GEMM, LSTM cell step, vocabulary projection)
