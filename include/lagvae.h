@@ -197,6 +197,14 @@ int lagvae_text_outer_step(lagvae_text_plan* plan, const lagvae_text_params* par
                            float lr, int update_encoder, float* grad_ws, float* out_loss, float* out_scalars,
                            void* stream);
 
+/* The decoder weights do not change inside the aggressive loop (text.py:387 steps the encoder only), so their bf16 hi/lo
+ * tensor-core operand copies (W_pred 82 MB, the x-columns of the decoder W_ih) need not be re-split at every inner step.
+ * The caller declares an EPOCH for the decoder weights: while consecutive calls on this plan see the same non-zero epoch the
+ * cached splits are reused; any change of the value (or 0 = "unknown, never cache", the default) re-splits.  The host side
+ * derives the epoch from the tensors' data pointers and torch version counters, which every in-place update bumps
+ * (optimizer steps, load_state_dict); lagvae_text_outer_step invalidates the cache itself. */
+int lagvae_text_decoder_weights_epoch(lagvae_text_plan* plan, uint64_t epoch);
+
 /* Data-parallel overlap hook (no counterpart in the single-process reference).  The decoder
  * gradients (the last 7 tensors of vae.parameters(), 70% of the bucket) are final before the encoder LSTM
  * backward starts.  With the hook enabled lagvae_text_loss_backward records an internal event at that

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-for p in 0 1000 2000 3000 4000; do echo "== poll sleep ns $p"; LAGVAE_LSTM_POLL_SLEEP_NS=$p python scripts/lstm_trace.py > gpurun_out/trace_p$p.log 2>&1; grep -E "kernel:|cell done|next step" gpurun_out/trace_p$p.log; done
+for cs in 2 4; do for n in 2 4; do echo "== fwd cs $cs bulk $n"; LAGVAE_LSTM_FWD_CS=$cs LAGVAE_LSTM_BULK_STAGES=$n python scripts/lstm_trace.py > gpurun_out/trace_cs${cs}_b$n.log 2>&1; grep -E "forward kernel:|first stage|MMAs issued|accumulators|partials|cluster barrier|cell done|next step" gpurun_out/trace_cs${cs}_b$n.log | head -8; done; done

@@ -27,6 +27,7 @@
 //   P16 P11 + P12: staggered start, 4 x 16 KB copies
 //   P20/P21/P22 = P9 / P15 / P6 with the operand written to 4 replicas (different addresses -> different L2 slices); a consumer
 //       reads replica (cta / 2) % 4: every line is read by 16 SMs instead of 64 (tests the L2 hot-spot hypothesis)
+//   P23a/b/c clusters of 1 / 2 / 4 CTAs that consume the SAME K slice: every member loads 1/CS of it with a multicast bulk copy
 //   P18 P15 while another warp spins on ld.acquire.gpu of the counter (next step's target) during the copy
 //   P19 P18 with the spinning warp using ld.relaxed.gpu + nanosleep(64)
 //   P17 validity-in-data: no counter, no release, no global fence.  Producers write whole 16-B chunks whose first bf16 carries
@@ -640,6 +641,118 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_probe3(const Args a) {
   if (errs) atomicAdd(a.errors, errs);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// P23/P24: cluster multicast.  Clusters of CS CTAs whose members need the SAME K slice (rank = cluster index & 1): every member
+// loads 1/CS of the 64 KB slice with cp.async.bulk ... .multicast::cluster into ALL members' rings, so the slice crosses the
+// L2 -> SM fabric once per cluster instead of once per CTA.  Counter protocol as P6 (consumer-side .global proxy fence).
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+template <int CS>
+__global__ void __launch_bounds__(NTHREADS, 1) k_probe_mc(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t ring = base;
+  const uint32_t bars = ring + NS * 2 * PART_BYTES;
+  const uint32_t full0 = bars;                      // ONE barrier for the whole slice: CS multicast copies complete_tx on it
+  const uint32_t done_bar = bars + 8u * (2 * NS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();
+  const int cl = blockIdx.x / CS;
+  const int rank = cl & 1;                          // K slice this whole cluster consumes
+  const int u0 = blockIdx.x * 8;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(full0, 1);
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  constexpr size_t SLOT_BYTES = (size_t)16 * 2 * PART_BYTES;
+  constexpr uint32_t STAGE_BYTES = 2 * PART_BYTES, SLICE = KB * STAGE_BYTES, PIECE = SLICE / CS;
+  uint8_t* gbase = (uint8_t*)a.abuf;
+  const bool tr = a.trace != nullptr && blockIdx.x == 0;
+  unsigned errs = 0;
+  uint32_t phase = 0;
+  for (int s = 0; s <= a.steps; ++s) {
+    if (s > 0) {
+      const uint8_t* src = gbase + (size_t)((s - 1) & (NSLOT - 1)) * SLOT_BYTES + (size_t)rank * SLICE;
+      if (warp == 5) {
+        if (lane == 0) {
+          const unsigned target = (unsigned)s * G;
+          unsigned spins = 0;
+          while (ld_acquire_u32(a.counter) < target) if (++spins > (1u << 24)) asm volatile("trap;");
+        }
+        __syncwarp();
+        if (tr && lane == 0) a.trace[s * 8 + 1] = clock64();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(full0, SLICE);                                   // all CS pieces land here (own + peers' multicasts)
+          bulk_g2s_mc(ring + crank * PIECE, src + (size_t)crank * PIECE, PIECE, full0, (uint16_t)((1u << CS) - 1));
+        }
+        __syncwarp();
+      } else if (warp == 4) {
+        ptx::mbar_wait(full0, phase);
+        if (tr && lane == 0) a.trace[s * 8 + 2] = clock64();
+        for (int kb = 0; kb < KB; ++kb)
+          for (int part = 0; part < 2; ++part) {
+            const uint8_t* tile = gen + (kb * STAGE_BYTES + part * PART_BYTES);
+            const int c = 3;
+            const uint4 v = *(const uint4*)(tile + lane * 128 + ((c ^ (lane & 7)) << 4));
+            const int ug = (rank * KB + kb) * 64 + c * 8;
+            if ((unsigned short)(v.x & 0xffff) != bf16_bits(s - 1, part, lane, ug)) ++errs;
+          }
+        __syncwarp();
+        phase ^= 1u;
+        if (tr && lane == 0) a.trace[s * 8 + 3] = clock64();
+        if (lane == 0) ptx::mbar_arrive(done_bar);
+      }
+      if (warp < 4) ptx::mbar_wait(done_bar, (uint32_t)((s - 1) & 1));
+      // a peer may only overwrite my ring (next step's multicast) after I have consumed this step's data
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (s == a.steps) break;
+    if (warp < 4) {
+      if (a.delay > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.delay) {
+        }
+      }
+      if (tr && threadIdx.x == 0) a.trace[s * 8 + 4] = clock64();
+      uint8_t* wslot = gbase + (size_t)(s & (NSLOT - 1)) * SLOT_BYTES + (size_t)(blockIdx.x / 8) * STAGE_BYTES;
+      const int c = blockIdx.x & 7;
+      if (threadIdx.x < 64) {
+        const int b = threadIdx.x >> 1, uq = threadIdx.x & 1, ub = u0 + uq * 4;
+        uint2 hi, lo;
+        hi.x = bf16_bits(s, 0, b, ub) | ((uint32_t)bf16_bits(s, 0, b, ub + 1) << 16);
+        hi.y = bf16_bits(s, 0, b, ub + 2) | ((uint32_t)bf16_bits(s, 0, b, ub + 3) << 16);
+        lo.x = bf16_bits(s, 1, b, ub) | ((uint32_t)bf16_bits(s, 1, b, ub + 1) << 16);
+        lo.y = bf16_bits(s, 1, b, ub + 2) | ((uint32_t)bf16_bits(s, 1, b, ub + 3) << 16);
+        const uint32_t off = (uint32_t)(b * 128 + ((c ^ (b & 7)) << 4) + uq * 8);
+        *(uint2*)(wslot + off) = hi;
+        *(uint2*)(wslot + PART_BYTES + off) = lo;
+      }
+      if (tr && threadIdx.x == 0) a.trace[s * 8 + 5] = clock64();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.counter) : "memory");
+        if (tr) a.trace[s * 8 + 6] = clock64();
+      }
+    }
+  }
+  if (errs) atomicAdd(a.errors, errs);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -713,6 +826,58 @@ static void run(const char* name, Args a, const Maps& tm, int steps) {
          name, best * 1e3 / steps, errs, d_f / n, d_s / n, d_seen / n, d_first / n, d_all / n, d_loop / n, d_cf / n);
 }
 
+template <int CS>
+static void run_mc(const char* name, Args a, int steps) {
+  const size_t smem = NS * 2 * PART_BYTES + 1024 + 8 * (2 * NS + 2) + 1024 + 64 + g_smem_pad;
+  auto kfn = k_probe_mc<CS>;
+  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaMemset(a.counter, 0, 256));
+    CK(cudaMemset(a.errors, 0, 4));
+    CK(cudaMemset(a.trace, 0, (size_t)(steps + 1) * 8 * 8));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernelEx(&cfg, kfn, a));
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  unsigned errs = 0;
+  CK(cudaMemcpy(&errs, a.errors, 4, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> tr((size_t)(steps + 1) * 8);
+  CK(cudaMemcpy(tr.data(), a.trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+  double d_s = 0, d_seen = 0, d_first = 0, d_loop = 0;
+  int n = 0;
+  for (int s = 5; s + 1 < steps; ++s) {
+    const unsigned long long t4 = tr[s * 8 + 4];
+    d_s += (double)(tr[s * 8 + 6] - t4);
+    d_seen += (double)(tr[(s + 1) * 8 + 1] - t4);
+    d_first += (double)(tr[(s + 1) * 8 + 2] - t4);
+    d_loop += (double)(tr[(s + 1) * 8 + 4] - t4);
+    ++n;
+  }
+  printf("%-44s %8.3f us/step  errors %u | CTA0 cycles from store start: signal %5.0f seen %5.0f slice landed %5.0f loop %5.0f\n", name,
+         best * 1e3 / steps, errs, d_s / n, d_seen / n, d_first / n, d_loop / n);
+}
+
 int main(int argc, char** argv) {
   const int steps = argc > 1 ? atoi(argv[1]) : 400;
   const int delay = argc > 2 ? atoi(argv[2]) : 0;
@@ -758,6 +923,9 @@ int main(int argc, char** argv) {
   run<20, true>("P20 P9 (1 x 64KB bulk) + 4 replicas", a, tm, steps);
   run<21, true>("P21 P15 (LDG copy) + 4 replicas", a, tm, steps);
   run<22, true>("P22 P6 (8 x 8KB bulk) + 4 replicas", a, tm, steps);
+  run_mc<1>("P23a cluster 1 (unicast 64KB, .global fence)", a, steps);
+  run_mc<2>("P23b cluster 2, 2 x 32KB multicast", a, steps);
+  run_mc<4>("P23c cluster 4, 4 x 16KB multicast", a, steps);
   run<18, true>("P18 P15 + concurrent ld.acquire spinner", a, tm, steps);
   run<19, true>("P19 P15 + relaxed/nanosleep spinner", a, tm, steps);
   return 0;

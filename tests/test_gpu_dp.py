@@ -162,3 +162,34 @@ def test_library_owned_nccl_bucket_allreduce_matches_torch():
         assert pr.exitcode == 0
     for rank, ok in res.items():
         assert ok is True or ok < 1e-6, (rank, ok)         # NCCL's ring order may differ in the last bit between communicators
+
+
+def test_unmodified_text_py_spmd_on_two_gpus(tmp_path):
+    """SURVEY §8 b3 at script level: the unmodified text.py started once per GPU (torchrun) through the driver shim; both
+    ranks print the same log (identical control flow: Σloss, break rule, batch picks agree) and it follows the single-GPU
+    run of the same back-end to the tight-prefix bar of tests/test_gpu_reference_drivers.py."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_reference_drivers as D
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if D.ref_dir() is None:
+        pytest.skip("reference scripts not staged (scripts/stage_reference.sh)")
+    wd = D.make_workdir(str(tmp_path / "run"))
+    args = ["--dataset", "tinysyn"] + D.TEXT_ARGS
+    rc1, out1 = D.run_driver("text.py", "lagvae", args, wd, 900)
+    assert rc1 == 0, out1[-3000:]
+    env = dict(os.environ, LAGVAE_RUN_DIR=wd, PYTHONWARNINGS="ignore")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(36000 + os.getpid() % 2000), os.path.join(ROOT, "scripts", "run_reference_driver.py"),
+           "--backend", "lagvae", "--extra-path", D.DRV, os.path.join(D.ref_dir(), "text.py")] + args
+    r = subprocess.run(cmd, env=env, cwd=wd, capture_output=True, text=True, timeout=1200)
+    D.save("text_tinysyn_lagvae_2gpu.log", r.stdout + "\n" + r.stderr)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    logs = []
+    for sub in ("", "rank1"):
+        with open(os.path.join(wd, sub, "logs", "tinysyn", "tinysyn_aggressive1_kls0.10_warm10_0_0_783435.log")) as f:
+            logs.append(D.parse(f.read()))
+    strip = lambda rows: [(k, {f: v for f, v in d.items()}) for k, d in rows]
+    assert strip(logs[0]) == strip(logs[1]), "the two ranks printed different numbers"
+    D.compare_logs(logs[0], D.parse(out1), "text.py tinysyn: 2 GPUs (SPMD) vs 1 GPU", n_tight=6, rel_tight=2e-3)

@@ -249,3 +249,22 @@ def test_image_eval_mode_vs_reference_golden(golden):
     assert_close(rec, g["rec"], 1e-4, "rec (eval)")
     assert_close(kl, g["kl"], 1e-4, "kl (eval)", floor=1e-2)
     assert_close(rec + float(g["kl_weight"]) * kl, g["loss"], 1e-4, "loss (eval)")
+
+
+def test_outgrown_buffers_are_retired_while_a_graph_is_alive():
+    """a captured graph bakes raw pointers into the scratch buffers; a later, larger eager call must not free them."""
+    import lagvae
+    import lagvae.graph as G
+    from modules import image as I
+    dev = torch.device("cuda")
+    x = torch.zeros(4, device=dev)
+    step = lagvae.GraphedStep(lambda x: x * 2.0, {"x": x}, warmup=1)
+    tag = "test-retire"
+    a = I._scratch(1 << 20, tag, dev)
+    ptr = a.data_ptr()
+    del a
+    n0 = len(G._RETIRED)
+    b = I._scratch(8 << 20, tag, dev)                      # outgrows the buffer while `step` is alive
+    assert len(G._RETIRED) == n0 + 1 and G._RETIRED[-1].data_ptr() == ptr and b.data_ptr() != ptr
+    assert float(step(x=torch.ones(4, device=dev)).sum()) == 8.0
+    del step

@@ -1,8 +1,10 @@
 """Parity of the CUDA hot path (through the C-ABI / drop-in modules) against the oracle and the golden
 fixtures produced by the unmodified reference.  Tolerances: outputs (loss/rec/KL/MI) 1e-4 relative
-(north_star); gradients 2e-3 of the tensor's max (fp32 accumulation-order noise over ~1e4-term sums,
-split-bf16 operands on the tensor-core path); KL/MI use an absolute floor because fp32 KL is
-ill-conditioned near 0 (SURVEY §7 hard part 3)."""
+(north_star); gradients 2e-4 of the tensor's max (measured worst on these fixtures: 4.2e-5, both kernel
+tiers — scripts/grad_error_report.py, profiles/r2_grad_errors.md; fp32 accumulation-order noise, split-bf16
+operands on the tensor-core path); KL/MI use an absolute floor because fp32 KL is ill-conditioned near 0
+(SURVEY §7 hard part 3).  The full-shape tests (6 368-term sums, 200 dependent LSTM steps) keep their own,
+looser bar: gradient norms 2e-3, strided samples 5e-3 (tests/test_gpu_benchmarked_config.py)."""
 import os
 import types
 
@@ -15,7 +17,7 @@ from util import FULL_CASES, assert_close, case_inputs, case_params
 
 pytestmark = pytest.mark.gpu
 OUT_TOL = 1e-4
-GRAD_TOL = 2e-3
+GRAD_TOL = 2e-4      # measured worst: 4.2e-5 of the tensor maximum (profiles/r2_grad_errors.md)
 
 
 def _engine(c, force_simt):
@@ -472,3 +474,41 @@ def test_decoder_update_step_matches_oracle(golden, name, update_encoder):
             assert torch.allclose(q.detach(), before[k] - grads[k], rtol=0, atol=1e-7 * float(before[k].abs().max()) + 1e-12), k
         else:
             assert torch.equal(q.detach(), before[k]), k
+
+
+def test_decoder_weight_split_cache_follows_the_weights(golden):
+    """The bf16 hi/lo copies of the decoder weights are cached across calls while the weights' epoch (data pointers + torch
+    version counters + liblagvae's own in-place updates) is unchanged: results must track every kind of update."""
+    g = golden("aligned_train")
+    c = case_inputs(g)
+    p = case_params(g)
+    eng = _engine(c, False)
+    params = _plist(p)
+    x, eps = c["x"].cuda(), c["eps"].cuda()
+    want0 = O.vae_loss(p, c["x"], c["klw"], c["eps"])[0]
+    for _ in range(2):                                           # second call runs on the cached splits
+        assert_close(eng.loss_forward(params, x, eps, c["klw"])[0], want0, OUT_TOL, "loss (cache warm)")
+    # (1) in-place torch update of a decoder weight (what dec_optimizer.step() does)
+    with torch.no_grad():
+        params[12].mul_(1.5)
+        params[8].add_(0.01)
+    p2 = {k: q.cpu().clone() for k, q in zip(O.ALL_KEYS, params)}
+    assert_close(eng.loss_forward(params, x, eps, c["klw"])[0], O.vae_loss(p2, c["x"], c["klw"], c["eps"])[0], OUT_TOL, "loss after torch update")
+    # (2) the library's own decoder step (outer_step) must invalidate too
+    gw = eng.grad_workspace()
+    out_loss, sc = torch.empty(c["B"], device="cuda"), torch.empty(4, device="cuda")
+    eng.outer_step(params, x, eps, c["klw"], None, gw, out_loss, sc, False)
+    p3 = {k: q.cpu().clone() for k, q in zip(O.ALL_KEYS, params)}
+    assert not torch.equal(p3["decoder.pred_linear.weight"], p2["decoder.pred_linear.weight"])
+    assert_close(eng.loss_forward(params, x, eps, c["klw"])[0], O.vae_loss(p3, c["x"], c["klw"], c["eps"])[0], OUT_TOL, "loss after outer_step")
+    # (2b) plans of different shapes share the workspace (and the cache at its start): alternate between two shapes
+    x_short = O.make_token_batch(c["B"], c["T"] - 3, c["V"], seed=5)
+    want_s = O.vae_loss(p3, x_short, c["klw"], c["eps"])[0]
+    want_l = O.vae_loss(p3, c["x"], c["klw"], c["eps"])[0]
+    for _ in range(2):
+        assert_close(eng.loss_forward(params, x_short.cuda(), eps, c["klw"])[0], want_s, OUT_TOL, "loss (short plan)")
+        assert_close(eng.loss_forward(params, x, eps, c["klw"])[0], want_l, OUT_TOL, "loss (long plan)")
+    # (3) a different tensor object with other values
+    params[12] = (params[12] * 0.5).contiguous()
+    p4 = {k: q.cpu().clone() for k, q in zip(O.ALL_KEYS, params)}
+    assert_close(eng.loss_forward(params, x, eps, c["klw"])[0], O.vae_loss(p4, c["x"], c["klw"], c["eps"])[0], OUT_TOL, "loss after re-binding")

@@ -731,6 +731,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
     };
     if (warp == 5) {
       // ------------------------------- producer: this CTA's K slice of the published operand, global (L2) -> ring
+      const int nst = KBS * a.m_tiles;
+      // While the other CTAs are still publishing: make sure the ring slots this step starts with are free (their MMAs of the
+      // previous step committed long ago).  Every mbarrier.try_wait costs ~90 cycles even when the phase is complete; done
+      // here they are off the critical path, done after the counter they delayed the first copy by 0.4-0.7 K cycles
+      // (probe P9 vs P23a: 2.7 K vs 1.4 K cycles from "seen" to 64 KB landed).
+      const int npre = has_rec ? min(nst, a.NS) : 0;
+      {
+        PipeState q = ps;
+        for (int j = 0; j < npre; ++j) {
+          ptx::mbar_wait(sm.empty(q.stage, a.NS), q.phase ^ 1u);
+          if (++q.stage == a.NS) { q.stage = 0; q.phase ^= 1u; }
+        }
+      }
       if (s > 0) {                       // every CTA has published its part of this step's operand
         if (lane == 0) {
           const unsigned target = (unsigned)(s + 1) * gridDim.x;
@@ -750,17 +763,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
         asm volatile("fence.proxy.async.global;" ::: "memory");
         // The K slice of this CTA is ONE contiguous region of the tile image (k-block major: stage i = kb * m_tiles + mt).  It
         // moves as a few LARGE cp.async.bulk copies of `a.bulk_stages` ring stages each: on this access pattern a bulk copy
-        // costs ~1.6 K cycles to its first byte and separate 8 KB copies retire one every ~0.7 K cycles, while 32 KB
-        // copies stream (probe P6 vs P12/P9).  The first stage of a group carries the group's transaction bytes; the MMA warp
-        // consumes stages in order, so it has passed the leader's barrier before it touches a later stage of the group.
-        const int nst = KBS * a.m_tiles;
+        // costs ~1.4 K cycles to land 64 KB but separate 8 KB copies retire only one every ~0.7 K cycles (probe P6 vs
+        // P23a).  The first stage of a group carries the group's transaction bytes; the MMA warp consumes stages in order,
+        // so it has passed the leader's barrier before it touches a later stage of the group.
         const uint8_t* gsrc = abuf8 + (size_t)rd_slot * slot_bytes_g + (size_t)rank * nst * stage_bytes;
         for (int i = 0; i < nst;) {
           const int glen = min(min(a.bulk_stages, nst - i), a.NS - ps.stage);     // contiguous in the ring, too
-          for (int j = 0; j < glen; ++j) {
-            int slot = ps.stage + j;                                           // no wrap inside a group
-            ptx::mbar_wait(sm.empty(slot, a.NS), ps.phase ^ 1u);
-          }
+          for (int j = 0; j < glen; ++j)
+            if (i + j >= npre) ptx::mbar_wait(sm.empty(ps.stage + j, a.NS), ps.phase ^ 1u);   // slot re-used within the step
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(sm.full(ps.stage), (uint32_t)glen * stage_bytes);
             bulk_g2s(sm.a_base + (uint32_t)ps.stage * stage_bytes, gsrc + (size_t)i * stage_bytes, (uint32_t)glen * stage_bytes,
@@ -788,24 +798,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
           ptx::tc_fence_after();
           if (trace && i == 0 && lane == 0) a.dbg[s * 8 + 1] = clock64();
           if (ptx::elect_one()) {
+            // the issue loop is the tensor pipe's feed: keep it to a few integer instructions per MMA.  A descriptor's start
+            // address field counts 16-byte units, so the four K sub-steps of a stage (32 bytes apart) are desc + 2 k.
+            int kb = i / a.m_tiles, mt = i - kb * a.m_tiles;
             for (int j = 0; j < glen; ++j) {
-              const int kb = (i + j) / a.m_tiles, mt = (i + j) - kb * a.m_tiles;
               const uint32_t d = tmem_base + (uint32_t)(mt * C::NALL);
               const uint32_t sa = sm.a_base + (uint32_t)(ps.stage + j) * 2 * a.part_bytes;
-              const uint32_t sw = sm.w_base + (uint32_t)kb * C::WT;
+              const uint64_t a_hi0 = ptx::make_smem_desc_sw128(sa, 16, 1024);
+              const uint64_t b0 = ptx::make_smem_desc_sw128(sm.w_base + (uint32_t)kb * C::WT, 16, 1024);
+              if (stack) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t a_hi = ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                const uint64_t a_lo = ptx::make_smem_desc_sw128(sa + a.part_bytes + k * 32, 16, 1024);
-                const uint64_t bdsc = ptx::make_smem_desc_sw128(sw + k * 32, 16, 1024);
-                ptx::umma_f16(d, a_hi, bdsc, idesc_all, (kb | k) ? 1u : 0u);
-                if (!stack) ptx::umma_f16(d, a_lo, bdsc, idesc_hi, 1u);
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(d, a_hi0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc_all, (kb | k) ? 1u : 0u);
+              } else {
+                const uint64_t a_lo0 = ptx::make_smem_desc_sw128(sa + a.part_bytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  ptx::umma_f16(d, a_hi0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc_all, (kb | k) ? 1u : 0u);
+                  ptx::umma_f16(d, a_lo0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc_hi, 1u);
+                }
               }
+              if (++mt == a.m_tiles) { mt = 0; ++kb; }
             }
+            kb = i / a.m_tiles;
+            mt = i - kb * a.m_tiles;
             for (int j = 0; j < glen; ++j) {
               ptx::umma_commit(sm.empty(ps.stage + j, a.NS));
-              const int kb = (i + j) / a.m_tiles;
-              if (kb == KBS - 1) ptx::umma_commit(sm.acc((i + j) - kb * a.m_tiles, a.NS));
+              if (kb == KBS - 1) ptx::umma_commit(sm.acc(mt, a.NS));
+              if (++mt == a.m_tiles) { mt = 0; ++kb; }
             }
           }
           __syncwarp();

@@ -3,6 +3,8 @@
 // kernels_simt.cu / gemm_tc.cu / lstm_tc.cu.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -42,6 +44,14 @@ struct lagvae_text_plan {
   // tensor-core operand arena (bf16 hi/lo staging), bump allocated per pass
   char* arena;
   size_t arena_bytes, arena_off;
+  // decoder weights do not change inside the aggressive loop (text.py:387 steps the encoder only): their bf16 hi/lo splits are
+  // cached across calls while the caller-declared epoch (lagvae_text_decoder_weights_epoch) stays the same; 0 = never cache
+  // The cache sits at the START of the workspace (same address for every plan of an engine: plans of different (B,T,ns)
+  // share one workspace) and its state is shared through a registry keyed by that address (WCacheState below).
+  char* wcache;
+  size_t wcache_bytes;
+  uint64_t dec_epoch;
+  struct WCacheState* wc;
   LstmTcState* lstm_tc;  // persistent tcgen05 LSTM state (nullptr when unsupported / SIMT)
   cudaEvent_t dec_ev;    // optional: recorded when the decoder gradients are final (data-parallel overlap hook)
   bool dec_ev_recorded;
@@ -58,7 +68,23 @@ struct lagvae_text_plan {
   int dec_wgrad_passes;  // 3 = fp32-grade; 1 = single bf16 pass (fused inner step: these gradients only feed the clip norm)
 };
 
+struct WCacheState {
+  uint64_t epoch = 0;            // epoch the cached splits belong to (0 = nothing cached)
+  bool filled[2] = {false, false};
+};
+
 namespace {
+
+std::mutex g_wc_mutex;
+std::map<void*, WCacheState*> g_wc_registry;   // workspace base -> shared cache state (entries live for the process)
+WCacheState* wcache_state_for(void* base) {
+  std::lock_guard<std::mutex> lk(g_wc_mutex);
+  auto it = g_wc_registry.find(base);
+  if (it != g_wc_registry.end()) return it->second;
+  WCacheState* s = new WCacheState();
+  g_wc_registry[base] = s;
+  return s;
+}
 
 struct Carver {
   char* base;
@@ -91,6 +117,10 @@ void carve(lagvae_text_plan* P, char* base) {
   const lagvae_text_dims& d = P->d;
   const int64_t B = d.B, Bd = P->Bd, re = P->re, rd = P->rd, nh = d.nh, ni = d.ni, nz = d.nz, V = d.V;
   Carver c{base, 0};
+  // first: the cross-call decoder-weight cache — its size depends on (V, ni, nh) only, so every plan of an engine finds it at
+  // the same address
+  P->wcache_bytes = P->use_tc ? (size_t)(((int64_t)4 * nh * round_up(ni, 8) + V * round_up(nh, 8)) * 2 * sizeof(uint16_t) + 2048) : 0;
+  P->wcache = c.take<char>((int64_t)P->wcache_bytes);
   P->xe = c.take<float>(re * ni);
   P->gates_e = c.take<float>(re * 4 * nh);
   P->c_e = c.take<float>(re * nh);
@@ -167,6 +197,32 @@ Staged stage(lagvae_text_plan* P, Mat m, cudaStream_t st, int* status) {
   P->arena_off = off + need;
   const int r = split_bf16_launch(m.p, m.ld, (int)m.rows, (int)m.cols, hi, lo, ldo, st);
   if (r != LAGVAE_OK) *status = r;
+  s.tc = TcOperand{hi, lo, ldo, 0};
+  return s;
+}
+
+// decoder weight operands through the cross-call cache: which = 0 -> x-columns of W_ih ([4nh, ni], ld ni+nz), 1 -> W_pred [V, nh]
+Staged stage_dec_weight(lagvae_text_plan* P, int which, Mat m, cudaStream_t st, int* status) {
+  if (!P->use_tc || P->dec_epoch == 0 || P->wc == nullptr) return stage(P, m, st, status);
+  WCacheState* wc = P->wc;
+  if (wc->epoch != P->dec_epoch) {         // the weights changed (or nothing cached yet): both entries are stale
+    wc->epoch = P->dec_epoch;
+    wc->filled[0] = wc->filled[1] = false;
+  }
+  const lagvae_text_dims& d = P->d;
+  const int64_t ld0 = round_up(d.ni, 8), ld1 = round_up(d.nh, 8);
+  uint16_t* base0 = (uint16_t*)P->wcache;
+  uint16_t* base1 = (uint16_t*)round_up((int64_t)(uintptr_t)(base0 + (int64_t)2 * 4 * d.nh * ld0), 256);
+  uint16_t* hi = which == 0 ? base0 : base1;
+  const int64_t ldo = which == 0 ? ld0 : ld1;
+  uint16_t* lo = hi + m.rows * ldo;
+  if (!wc->filled[which]) {                // filled on the first request within the epoch (same stream order as its readers)
+    const int r = split_bf16_launch(m.p, m.ld, (int)m.rows, (int)m.cols, hi, lo, ldo, st);
+    if (r != LAGVAE_OK) *status = r;
+    wc->filled[which] = true;
+  }
+  Staged s;
+  s.m = m;
   s.tc = TcOperand{hi, lo, ldo, 0};
   return s;
 }
@@ -338,7 +394,7 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
                   st));                                                                      // :100
   LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
   Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
-  Staged swd = stage(P, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
+  Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
   LV_TRY(status);
   LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
             3, st));
@@ -350,7 +406,7 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
                               st));                                                          // :104,106
   // vocabulary projection (:109) + cross entropy (:143-148)
   Staged sh = stage(P, Mat{hdrop ? hdrop : P->h_d, P->rd, nh, nh}, st, &status);
-  Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
+  Staged swp = stage_dec_weight(P, 1, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
   LV_TRY(status);
   LV_TRY(mm(P, sh, false, swp, false, P->logits, P->ldl, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
   if (with_ce) LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
@@ -440,6 +496,8 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
   }
   P->have_forward = false;
   P->dec_wgrad_passes = 3;
+  P->dec_epoch = 0;
+  P->wc = wcache_state_for(workspace);
   *out = P;
   return LAGVAE_OK;
 }
@@ -452,6 +510,12 @@ void lagvae_text_plan_destroy(lagvae_text_plan* P) {
   if (P->side_join) cudaEventDestroy(P->side_join);
   if (P->side) cudaStreamDestroy(P->side);
   delete P;
+}
+
+int lagvae_text_decoder_weights_epoch(lagvae_text_plan* P, uint64_t epoch) {
+  LV_CHECK_ARG(P, "decoder_weights_epoch: null plan");
+  P->dec_epoch = epoch;
+  return LAGVAE_OK;
 }
 
 int lagvae_text_decoder_grads_event(lagvae_text_plan* P, int enable) {
@@ -591,7 +655,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
       LV_TRY(ce_bwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, st));
       sdl = stage(P, Mat{P->logits, rd, V, P->ldl}, st, &status);
     }
-    Staged swp = stage(P, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
+    Staged swp = stage_dec_weight(P, 1, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
     Staged sh = stage(P, Mat{hd, rd, nh, nh}, st, &status);
     LV_TRY(status);
     // dH_drop [rd, nh] = dlogits · W_pred
@@ -633,7 +697,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     Staged sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
     Staged sxd = stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
     Staged shd = stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
-    Staged swx = stage(P, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
+    Staged swx = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
     LV_TRY(status);
     // dW_ih[:, :ni] = dGᵀ · X   ;  dW_ih[:, ni:] = dzbᵀ · z
     LV_TRY(mm(P, sdg, true, sxd, true, gr->p[D_WIH], ni + nz, 4 * nh, ni, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
@@ -778,8 +842,10 @@ int lagvae_text_outer_step(lagvae_text_plan* P, const lagvae_text_params* w, con
                            float lr, int update_encoder, float* grad_ws, float* out_loss, float* out_scalars,
                            void* stream) {
   LV_CHECK_ARG(P && w && x && eps && grad_ws && out_loss && out_scalars, "outer_step: null argument");
-  return text_step(P, w, x, eps, kl_weight, drop, max_norm, lr, update_encoder != 0, true, grad_ws, out_loss, out_scalars,
-                   stream);
+  const int r = text_step(P, w, x, eps, kl_weight, drop, max_norm, lr, update_encoder != 0, true, grad_ws, out_loss,
+                          out_scalars, stream);
+  if (P->wc) P->wc->epoch = 0;   // the decoder weights were just stepped in place: whatever epoch the caller declares next, re-split
+  return r;
 }
 
 size_t lagvae_lstm_workspace_bytes(int nh, int Bd) {

@@ -83,6 +83,7 @@ PROTOTYPES = {
                                     _vp, _vp, _vp, _vp]),
     "lagvae_text_outer_step": (_i, [_vp, C.POINTER(TextParams), _vp, _vp, _f, C.POINTER(Dropout), _f, _f, _i,
                                     _vp, _vp, _vp, _vp]),
+    "lagvae_text_decoder_weights_epoch": (_i, [_vp, _u64]),
     "lagvae_text_decoder_grads_event": (_i, [_vp, _i]),
     "lagvae_text_wait_decoder_grads": (_i, [_vp, _vp]),
     "lagvae_lstm_workspace_bytes": (_sz, [_i, _i]),

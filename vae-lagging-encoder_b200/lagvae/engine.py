@@ -47,6 +47,10 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+import itertools
+_ENGINE_UID = itertools.count(1)
+
+
 class TextEngine:
     """One engine per (V, ni, nh, nz, device).  Plans (per B, T, ns) share one workspace that grows
     to the largest shape seen; only the most recent forward's stash is alive."""
@@ -66,6 +70,9 @@ class TextEngine:
         self.counts = [int(torch.Size(s).numel()) for s in self.shapes]
         self._ws = None
         self._plans = {}
+        self._uid = next(_ENGINE_UID)
+        self._ws_generation = 0   # bumped whenever the workspace is re-allocated: the cache inside it is gone
+        self._dec_bump = 0     # decoder-weight updates made by liblagvae.so itself (outer_step): part of the weight epoch
         self._hooked = set()   # (B, T, ns) keys whose plans record the decoder-gradient event: re-applied when plans are re-created
         self.last_ns = 1
         self.generation = 0  # bumped by every forward; backward must match
@@ -98,8 +105,11 @@ class TextEngine:
             raise be.LagvaeError("unsupported text dims %r" % (key,))
         if self._ws is None or self._ws.numel() < need:
             self._drop_plans()
+            from .graph import retire
+            retire(self._ws)           # a live CUDA graph may still hold pointers into the outgrown workspace
             self._ws = None
             self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            self._ws_generation += 1
         out = C.c_void_p()
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_plan_create(C.byref(d), self.flags, C.c_void_p(self._ws.data_ptr()),
@@ -124,6 +134,23 @@ class TextEngine:
                     what, i, PARAM_NAMES[i], tuple(shp), self.device, t.dtype, tuple(t.shape), t.device))
             tp.p[i] = t.data_ptr()
         return tp
+
+    def _declare_decoder_epoch(self, plan, params):
+        """Tell the plan whether the decoder weights changed since its last call (include/lagvae.h,
+        lagvae_text_decoder_weights_epoch): the epoch is derived from the data pointers and torch's version counters of the
+        7 decoder tensors — every in-place update (optimizer step, load_state_dict, copy_) bumps a counter — plus a counter
+        for the updates liblagvae.so makes itself (outer_step), which torch cannot see."""
+        dec = params[N_ENC:]
+        if any(t is None for t in dec):
+            epoch = 0
+        else:
+            # engine uid + workspace generation: a NEW engine / workspace must never hit a cache entry that an earlier one
+            # left behind at a recycled address (the allocator hands freed workspaces and tensors out again)
+            h = self._dec_bump * 1000003 + self._uid * 998244353 + self._ws_generation * 7919
+            for t in dec:
+                h = (h * 1000003 + t.data_ptr() * 31 + t._version) & (2 ** 63 - 1)
+            epoch = h | 1
+        be.check(be.lib().lagvae_text_decoder_weights_epoch(plan, C.c_uint64(epoch)), "lagvae_text_decoder_weights_epoch")
 
     def _x(self, x):
         if x.device != self.device or x.dtype != torch.int64 or x.dim() != 2:
@@ -157,6 +184,7 @@ class TextEngine:
         drop = self._check_drop(drop, B, T, ns)
         tp = self._params(params)
         h = self.plan(B, T, ns)
+        self._declare_decoder_epoch(h, params)
         out = [torch.empty(B, dtype=torch.float32, device=self.device) for _ in range(3)]
         mu = logvar = z = None
         if want_stats:
@@ -188,6 +216,7 @@ class TextEngine:
         gl, gr, gk = (self._f32(g, (B,), n) for g, n in ((g_loss, "g_loss"), (g_rec, "g_rec"), (g_kl, "g_kl")))
         grads = grads_out if grads_out is not None else [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.shapes]
         tg = self._params(grads, "grads")
+        self._declare_decoder_epoch(self.plan(B, T, ns), params)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_loss_backward(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(gl),
                                                         be.ptr(gr), be.ptr(gk), C.byref(tg),
@@ -218,6 +247,7 @@ class TextEngine:
         out = torch.empty(B, ns, dtype=torch.float32, device=self.device)
         dc = drop.to_c()
         self.generation += 1
+        self._declare_decoder_epoch(self.plan(B, T, ns), params)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_reconstruct_error(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(z),
                                                             C.byref(dc), be.ptr(out), _stream()),
@@ -236,6 +266,7 @@ class TextEngine:
         out = torch.empty(B * ns, Td, self.V, dtype=torch.float32, device=self.device)
         dc = drop.to_c()
         self.generation += 1
+        self._declare_decoder_epoch(self.plan(B, Td + 1, ns), params)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_decode_logits(self.plan(B, Td + 1, ns), C.byref(tp), be.ptr(src), be.ptr(z),
                                                         C.byref(dc), be.ptr(out), _stream()), "lagvae_text_decode_logits")
@@ -306,6 +337,7 @@ class TextEngine:
         tp = self._params(params)
         dc = drop.to_c()
         self.generation += 1
+        self._declare_decoder_epoch(self.plan(B, T, ns), params)
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_inner_step(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(eps),
                                                      float(kl_weight), C.byref(dc), float(max_norm), float(lr),
@@ -323,6 +355,8 @@ class TextEngine:
         tp = self._params(params)
         dc = drop.to_c()
         self.generation += 1
+        self._declare_decoder_epoch(self.plan(B, T, ns), params)
+        self._dec_bump += 1                       # this call steps the decoder weights in place
         with torch.cuda.device(self.device):
             be.check(be.lib().lagvae_text_outer_step(self.plan(B, T, ns), C.byref(tp), be.ptr(x), be.ptr(eps),
                                                      float(kl_weight), C.byref(dc), float(max_norm), float(lr),

@@ -7,10 +7,31 @@ few microseconds each plus ~120 autograd nodes, and the eager loop is host-bound
 torch op — and replays it per step: inputs are copied into static tensors, outputs are read from static tensors.
 
 Constraints (those of torch.cuda.graph): fixed shapes; optimizers constructed with `capturable=True`; nothing inside the
-body may synchronise (read Σloss from the returned static tensor AFTER the replay, as text.py:381 does with `.item()`)."""
+body may synchronise (read Σloss from the returned static tensor AFTER the replay, as text.py:381 does with `.item()`).
+
+Two more, specific to this library:
+* a captured graph holds RAW device pointers into the engine workspace / the image scratch buffers.  Those buffers grow on
+  demand (a larger eager call later, e.g. `nll_iw` on B*ns rows); while any GraphedStep is alive a buffer that is outgrown is
+  RETIRED (kept allocated, `retire()` below) instead of freed, so a replay never writes freed memory;
+* host scalars are frozen at capture.  That includes the Philox dropout seed of the text decoder: capturing a text model in
+  train() mode with in-kernel dropout would replay ONE mask for ever, so `modules.text.dropout_spec` refuses to build a Philox
+  spec while a stream is capturing (use eval(), p = 0, or LAGVAE_DROPOUT=torch masks drawn outside the graph)."""
+import weakref
 from typing import Callable, Dict, Sequence, Union
 
 import torch
+
+_LIVE = weakref.WeakSet()      # GraphedStep objects that are alive
+_RETIRED = []                  # outgrown buffers kept allocated while a graph may still reference them
+
+
+def retire(t):
+    """Called by the buffer owners (TextEngine.plan, modules.image._scratch) INSTEAD of dropping an outgrown buffer."""
+    if len(_LIVE) > 0 and t is not None:
+        _RETIRED.append(t)
+    elif len(_LIVE) == 0:
+        _RETIRED.clear()
+
 
 
 class GraphedStep:
@@ -32,6 +53,7 @@ class GraphedStep:
             out = body(**self.static_in)
         self._single = isinstance(out, torch.Tensor)
         self.static_out = [out] if self._single else list(out)
+        _LIVE.add(self)
 
     def __call__(self, **inputs: torch.Tensor):
         for k, v in inputs.items():

@@ -26,6 +26,8 @@ def _scratch(nbytes, tag, device):
     key = (tag, device.index if device.index is not None else torch.cuda.current_device())
     t = _SCRATCH.get(key)
     if t is None or t.numel() < nbytes:
+        from lagvae.graph import retire
+        retire(t)                      # a live CUDA graph may still hold pointers into the outgrown buffer (lagvae/graph.py)
         t = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
         _SCRATCH[key] = t
     return t

@@ -60,6 +60,9 @@ def dropout_spec(dec, B, T, ns, device, row_offset=0, rows_total=None):
         m_in = (torch.rand(total, T - 1, dec.ni, device=device) >= p_in).to(torch.uint8)[lo:hi].contiguous() if p_in > 0 else None
         m_out = (torch.rand(total * ns, T - 1, dec.nh, device=device) >= p_out).to(torch.uint8)[lo * ns:hi * ns].contiguous() if p_out > 0 else None
         return DropoutSpec(1, p_in, p_out, m_in, m_out, 0)
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        raise LagvaeError("in-kernel (Philox) dropout cannot be captured in a CUDA graph: the seed is a host scalar and every "
+                          "replay would reuse one mask (lagvae/graph.py); use eval(), p = 0 or LAGVAE_DROPOUT=torch")
     _CALLS[0] += 1
     seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * 0xD1B54A32D192ED03 + int(row_offset) * 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
     return DropoutSpec(2, p_in, p_out, None, None, seed)
