@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-n
 echo "launch list exit $?"
 # (2) full capture of the tensor-core GEMMs of one step
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base function -k regex:'^k_gemm_tc' -s 16 -c 8 \
-    -o gpurun_out/prof_r1 -f python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-image > gpurun_out/prof_bench.log 2>&1
+    -o gpurun_out/prof_r2 -f python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-image > gpurun_out/prof_bench.log 2>&1
 echo "full capture exit $?"
 python scripts/lstm_trace.py > gpurun_out/trace.log 2>&1; tail -14 gpurun_out/trace.log
 ls -la gpurun_out/

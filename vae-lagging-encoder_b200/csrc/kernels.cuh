@@ -24,6 +24,7 @@ int vec_add(const float* a, const float* b, float* o, int n, cudaStream_t st);
 int tanh_copy(const float* a, float* o, int n, cudaStream_t st);
 int dc0_total(const float* dc_init, const float* dh_init, const float* h0, float* o, int n, cudaStream_t st);
 int time_sum(const float* src, int Tn, int Bd, int ncol, float* out, cudaStream_t st);
+int add_row_periodic(float* x, const float* bias, int64_t rows, int ncol, int period, cudaStream_t st);
 int logits_batch_major(const float* src, int64_t ld, int V, int Tn, int Bd, float* out, cudaStream_t st);
 int col_sum(const float* src, int rows, int ncol, float* out1, float* out2, cudaStream_t st);
 int ce_fwd(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd,

@@ -386,6 +386,28 @@ int reparam_kl_bwd(const float* dz, const float* eps, const float* mu, const flo
 // ---------------------------------------------------------------------------------------------
 // small element-wise helpers
 // ---------------------------------------------------------------------------------------------
+// x[r, :] += bias[r % period, :]  (ncol % 4 == 0, 16-byte aligned): the time-invariant z contribution of the decoder input
+// projection (dec_lstm.py:84,97) added in ONE streaming pass over the [T'*Bd, 4nh] pre-activations.  Doing it in the GEMM
+// epilogue (per-row bias loads + a runtime modulo per store) made that GEMM 2.1x slower (235 vs 110 us, profiles/r2_ncu_full.md).
+__global__ void __launch_bounds__(256) k_add_row_periodic(float* __restrict__ x, const float* __restrict__ bias, int64_t rows, int ncol,
+                                                          int period) {
+  const int64_t n4 = rows * (ncol >> 2);
+  const int c4 = ncol >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4);
+    float4 v = ((float4*)x)[i];
+    const float4 b = ((const float4*)bias)[(r % period) * c4 + c];
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    ((float4*)x)[i] = v;
+  }
+}
+int add_row_periodic(float* x, const float* bias, int64_t rows, int ncol, int period, cudaStream_t st) {
+  LV_CHECK_ARG((ncol & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)bias & 15) == 0, "add_row_periodic: needs 16-B aligned rows");
+  k_add_row_periodic<<<148 * 8, 256, 0, st>>>(x, bias, rows, ncol, period);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
 __global__ void k_vec_add(const float* a, const float* b, float* o, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) o[i] = a[i] + b[i];
 }

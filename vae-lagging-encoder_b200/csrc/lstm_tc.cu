@@ -1303,6 +1303,9 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   int v2cs = 0;
   if (want_cs == 2) { v2 = v2_geometry<true, 2>(s, Bd, &a, &smem); v2cs = v2 ? 2 : 0; }
   if (!v2) { v2 = v2_geometry<true, 4>(s, Bd, &a, &smem); v2cs = v2 ? 4 : 0; }
+  // clusters of 4 need CS x rows x 144 B of receive slots next to the 128 KB of resident weights: beyond 64 rows that no
+  // longer fits, clusters of 2 (half the receive slots) still do up to 128 rows — and beat the non-cluster v1 kernel by far
+  if (!v2 && want_cs != 2) { v2 = v2_geometry<true, 2>(s, Bd, &a, &smem); v2cs = v2 ? 2 : 0; }
   if (!v2) {
     a.KP = s->KPf; a.KB = s->KPf / 64;
     a.m_tiles = (int)cdiv(Bd, 64);

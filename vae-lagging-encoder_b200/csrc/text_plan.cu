@@ -62,6 +62,8 @@ struct lagvae_text_plan {
   cudaEvent_t side_fork, side_join;
   size_t arena_floor;    // staging below this offset is still read by the side stream
   // state carried from forward to backward
+  Staged st_xe, st_xd, st_h;   // forward's bf16 hi/lo operand copies of xe, xd and hdrop/h_d: the backward GEMMs reuse them
+  size_t fwd_arena_end;        // ... so the backward's bump allocation starts behind them
   lagvae_dropout drop;
   float kl_weight;
   bool have_forward;
@@ -110,6 +112,7 @@ size_t arena_need(const lagvae_text_dims& d) {
   el += re * pad8(4 * d.nh) + re * pad8(d.ni) + re * pad8(d.nh);  // dgates_e, xe, h_e
   el += 2 * ((int64_t)4 * d.nh * pad8(d.ni + d.nz) + (int64_t)4 * d.nh * pad8(d.nh));  // LSTM weights
   el += Bd * pad8(d.nh) * 4;
+  el += re * pad8(d.ni) + rd * pad8(d.ni) + rd * pad8(d.nh);   // forward's xe | xd | h copies kept alive under the backward pass
   return (size_t)el * 2 * sizeof(uint16_t) + (64 << 10);
 }
 
@@ -166,6 +169,14 @@ void carve(lagvae_text_plan* P, char* base) {
   P->arena = c.take<char>((int64_t)P->arena_bytes);
   c.off = (size_t)round_up((int64_t)c.off, 256);
   P->bytes = c.off;
+}
+
+// start of a forward-type entry point: nothing staged, nothing kept for a backward pass
+void reset_pass(lagvae_text_plan* P) {
+  P->arena_off = 0;
+  P->fwd_arena_end = 0;
+  P->st_xe = P->st_xd = P->st_h = Staged{Mat{nullptr, 0, 0, 0}, TcOperand{nullptr, nullptr, 0, 0}};
+  P->have_forward = false;
 }
 
 bool dims_ok(const lagvae_text_dims* d) {
@@ -359,11 +370,15 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   LV_TRY(embed_gather(x, d.T, 0, d.B, 1, P->Te, w->p[E_EMB], ni, spec_none(), P->xe, st));   // enc_lstm.py:58
   LV_TRY(vec_add(w->p[E_BIH], w->p[E_BHH], P->bsum_e, 4 * nh, st));
   Staged sx = stage(P, Mat{P->xe, P->re, ni, ni}, st, &status);
+  P->st_xe = sx;                                  // kept for the backward pass (dW_ih = dGᵀ·X)
+  const size_t keep = P->arena_off;
   Staged sw = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
   LV_TRY(status);
   // input projection for all steps (first half of nn.LSTM, enc_lstm.py:60)
   LV_TRY(mm(P, sx, false, sw, false, P->gates_e, 4 * nh, (int)P->re, 4 * nh, ni, 1.f, 0.f, P->bsum_e, nullptr,
             0, 3, st));
+  P->arena_off = keep;                            // the W_ih copy is dead once the GEMM is enqueued (stream order)
+  P->fwd_arena_end = keep;
   if (P->lstm_tc)
     LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[E_WHH], nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
                            P->Te, d.B, st));
@@ -394,10 +409,17 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
                   st));                                                                      // :100
   LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
   Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
+  P->st_xd = sxd;
   Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
   LV_TRY(status);
-  LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
-            3, st));
+  if (P->use_tc && sxd.tc.hi && swd.tc.hi) {
+    // tensor-core tier: plain GEMM, then the row-periodic z bias in one streaming pass (see k_add_row_periodic)
+    LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    LV_TRY(add_row_periodic(P->gates_d, P->zb, P->rd, 4 * nh, Bd, st));
+  } else {
+    LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
+              3, st));
+  }
   float* hdrop = dout.mode ? P->hdrop_d : nullptr;
   if (P->lstm_tc)
     LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st));
@@ -406,6 +428,8 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
                               st));                                                          // :104,106
   // vocabulary projection (:109) + cross entropy (:143-148)
   Staged sh = stage(P, Mat{hdrop ? hdrop : P->h_d, P->rd, nh, nh}, st, &status);
+  P->st_h = sh;
+  P->fwd_arena_end = P->arena_off;     // xe | xd | h stay alive for the backward pass
   Staged swp = stage_dec_weight(P, 1, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
   LV_TRY(status);
   LV_TRY(mm(P, sh, false, swp, false, P->logits, P->ldl, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
@@ -542,8 +566,7 @@ int lagvae_text_encode_stats(lagvae_text_plan* P, const lagvae_text_params* w, c
                              float* out_mu, float* out_logvar, void* stream) {
   LV_CHECK_ARG(P && w && x && out_mu && out_logvar, "encode_stats: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  P->arena_off = 0;
-  P->have_forward = false;
+  reset_pass(P);
   LV_TRY(encoder_forward(P, w, x, st));
   const float* h_last = P->h_e + (int64_t)(P->Te - 1) * P->d.B * P->d.nh;
   LV_TRY(head_reparam_kl(h_last, w->p[E_LIN], nullptr, P->d.B, P->d.nh, P->d.nz, 1, out_mu, out_logvar,
@@ -567,8 +590,7 @@ int lagvae_text_loss_forward(lagvae_text_plan* P, const lagvae_text_params* w, c
   LV_CHECK_ARG(dr.p_in < 1.f && dr.p_out < 1.f, "loss_forward: dropout p must be < 1");
   P->drop = dr;
   P->kl_weight = kl_weight;
-  P->arena_off = 0;
-  P->have_forward = false;
+  reset_pass(P);
   int status = LAGVAE_OK;
 
   // ---- encoder: enc_lstm.py:47-64 ; reparameterise + KL: encoder.py:40-79
@@ -595,8 +617,7 @@ int lagvae_text_reconstruct_error(lagvae_text_plan* P, const lagvae_text_params*
   lagvae_dropout dr{};
   if (drop) dr = *drop;
   LV_CHECK_ARG(dr.mode >= 0 && dr.mode <= 2 && dr.p_in < 1.f && dr.p_out < 1.f, "reconstruct_error: bad dropout");
-  P->arena_off = 0;
-  P->have_forward = false;
+  reset_pass(P);
   LV_TRY(decoder_forward(P, w, x, z, dr, st));
   LV_TRY(time_sum(P->loss_row, P->Td, P->Bd, 1, out_rec_rows, st));   // dec_lstm.py:148
   return LAGVAE_OK;
@@ -609,8 +630,7 @@ int lagvae_text_decode_logits(lagvae_text_plan* P, const lagvae_text_params* w, 
   lagvae_dropout dr{};
   if (drop) dr = *drop;
   LV_CHECK_ARG(dr.mode >= 0 && dr.mode <= 2 && dr.p_in < 1.f && dr.p_out < 1.f, "decode_logits: bad dropout");
-  P->arena_off = 0;
-  P->have_forward = false;
+  reset_pass(P);
   LV_TRY(decoder_forward(P, w, input, z, dr, st, P->Td, false));
   LV_TRY(logits_batch_major(P->logits, P->ldl, P->d.V, P->Td, P->Bd, out_logits, st));
   return LAGVAE_OK;
@@ -628,8 +648,8 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   const int64_t re = P->re, rd = P->rd;
   const DropSpec din = spec_in(P->drop), dout = spec_out(P->drop);
   int status = LAGVAE_OK;
-  P->arena_off = 0;
-  P->arena_floor = 0;
+  P->arena_off = P->fwd_arena_end;   // forward's copies of xe | xd | h stay alive below this offset
+  P->arena_floor = P->fwd_arena_end;
   P->have_forward = false;  // logits are consumed in place
   // norm-only dW_pred on a side stream under the decoder recurrence: OPT-IN (LAGVAE_SIDE_WGRAD=1).  Correct (the
   // full-shape fused-step test passes with it), but measured SLOWER on the B200: 10.22 vs 9.49 ms/step — the 20 GEMM CTAs
@@ -656,7 +676,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
       sdl = stage(P, Mat{P->logits, rd, V, P->ldl}, st, &status);
     }
     Staged swp = stage_dec_weight(P, 1, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
-    Staged sh = stage(P, Mat{hd, rd, nh, nh}, st, &status);
+    Staged sh = P->st_h.tc.hi ? P->st_h : stage(P, Mat{hd, rd, nh, nh}, st, &status);   // forward's copy of hdrop / h_d
     LV_TRY(status);
     // dH_drop [rd, nh] = dlogits · W_pred
     LV_TRY(mm(P, sdl, false, swp, true, P->dh_d, nh, (int)rd, nh, V, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
@@ -695,8 +715,9 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   LV_TRY(col_sum(P->dzb, Bd, 4 * nh, gr->p[D_BIH], gr->p[D_BHH], st));
   {
     Staged sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
-    Staged sxd = stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
-    Staged shd = stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
+    Staged sxd = P->st_xd.tc.hi ? P->st_xd : stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
+    // h_d itself (not its dropped-out version) pairs with dG in dW_hh: forward's copy serves only when dropout_out is off
+    Staged shd = (P->st_h.tc.hi && !dout.mode) ? P->st_h : stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
     Staged swx = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
     LV_TRY(status);
     // dW_ih[:, :ni] = dGᵀ · X   ;  dW_ih[:, ni:] = dzbᵀ · z
@@ -726,7 +747,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   if (side_pending) {   // dW_pred finished long ago (≈1.1 ms on 20 SMs vs 1.7 ms of recurrence): join, free its staging
     LV_CUDA(cudaStreamWaitEvent(st, P->side_join, 0));
     side_pending = false;
-    P->arena_floor = 0;
+    P->arena_floor = P->fwd_arena_end;
   }
   // all 7 decoder gradients are final here: data-parallel callers may start reducing them (lagvae.h)
   if (P->dec_ev) {
@@ -743,7 +764,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
                   0, st));
 
   // ---- encoder LSTM backward
-  P->arena_off = 0;
+  P->arena_off = P->fwd_arena_end;
   if (P->lstm_tc)
     LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
                             P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, false, st));
@@ -754,7 +775,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   LV_TRY(col_sum(P->dzb, B, 4 * nh, gr->p[E_BIH], gr->p[E_BHH], st));
   {
     Staged sdg = stage(P, Mat{P->dgates_e, re, 4 * nh, 4 * nh}, st, &status);
-    Staged sxe = stage(P, Mat{P->xe, re, ni, ni}, st, &status);
+    Staged sxe = P->st_xe.tc.hi ? P->st_xe : stage(P, Mat{P->xe, re, ni, ni}, st, &status);
     Staged she = stage(P, Mat{P->h_e, re, nh, nh}, st, &status);
     Staged swx = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
     LV_TRY(status);
