@@ -58,6 +58,10 @@ struct RecArgs {
   float* dh_rec_out;             // [Bd, nh] (d h_{-1}) when want_init
   float* dgates;                 // [Tn*Bd, 4nh]
   int want_init;
+  float* dgsum;                  // backward, optional: [Bd, 4nh] = sum over time of dG (the bias gradients' and dz's input), accumulated in
+                                 // registers across the steps and written once — replaces a 105 MB re-read of dgates (time_sum)
+  __nv_bfloat16* dg_hi;          // backward, optional: dG as the bf16 hi / lo tensor-core operand [Tn*Bd, 4nh] of the weight-gradient
+  __nv_bfloat16* dg_lo;          // GEMMs, written next to the fp32 copy — replaces a k_split_bf16 pass over dgates
   int bulk_stages;               // v2: ring stages per cp.async.bulk copy (LAGVAE_LSTM_BULK_STAGES, default 4)
   int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
 };
@@ -680,6 +684,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
   const bool trace = a.dbg != nullptr && blockIdx.x == 0;
   const int nsteps = FWD ? Tn : Tn + (a.want_init ? 1 : 0);
   int acc_par = 0;
+  float dgs[16];                 // backward: running sum over time of this thread's 16 dG values (single-item threads only)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) dgs[j] = 0.f;
   // Per-step synchronisation (no CTA-wide barrier inside the loop): the epilogue warps arrive on the grid counter as
   // soon as the next operand is stored; only the TMA producer warp polls it.  The MMA warp is gated by the ring's
   // mbarriers, the epilogue warps by the accumulator mbarrier, and every re-use (TMEM accumulator, receive slots,
@@ -996,10 +1003,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
           if (t < 0) {
             *(float4*)(a.dh_rec_out + (int64_t)b * nh + ub) = make_float4(rec[0], rec[1], rec[2], rec[3]);
           } else {
-            float* go = a.dgates + ((int64_t)t * Bd + b) * 4 * nh + ub;
+            const int64_t go_off = ((int64_t)t * Bd + b) * 4 * nh + ub;
+            float* go = a.dgates + go_off;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *(float4*)(go + q * nh) = make_float4(dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]);
+            if (a.dg_hi) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float seg[4] = {dg[q * 4], dg[q * 4 + 1], dg[q * 4 + 2], dg[q * 4 + 3]};
+                store_bf16x4(a.dg_hi + go_off + q * nh, a.dg_lo + go_off + q * nh, seg);
+              }
+            }
+            if (a.dgsum) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dgs[j] += dg[j];
+            }
             *(float4*)(a.dc + (int64_t)b * nh + ub) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
           }
         };
@@ -1064,6 +1083,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
         if (defer && (int)threadIdx.x < items) store_rest((int)threadIdx.x);
       }
     }
+  }
+  if (!FWD && a.dgsum && warp < 4 && (int)threadIdx.x < Bd * 2) {     // host side guarantees Bd * 2 <= 128 when dgsum is requested
+    const int b = (int)threadIdx.x >> 1, ub = u0 + ((int)threadIdx.x & 1) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *(float4*)(a.dgsum + (int64_t)b * 4 * nh + q * nh + ub) = make_float4(dgs[q * 4], dgs[q * 4 + 1], dgs[q * 4 + 2], dgs[q * 4 + 3]);
   }
   cluster_sync_all();                              // no CTA may exit while a peer can still read its shared memory
   if (warp == 4) tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
@@ -1347,7 +1372,9 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
 
 int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
                      const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
-                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st) {
+                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st, float* dgsum,
+                     uint16_t* dg_hi, uint16_t* dg_lo, bool* extras_done) {
+  if (extras_done) *extras_done = false;
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_backward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
@@ -1371,6 +1398,11 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.c0 = c0; a.gates = const_cast<float*>(gates);
   a.c_all = const_cast<float*>(c_all); a.dh_ext = dh_ext; a.drop = drop; a.dh_last = dh_last; a.dc = dc;
   a.dh_rec_out = dh_rec; a.dgates = dgates; a.want_init = want_init ? 1 : 0;
+  // the in-kernel extras (time sum of dG, dG as bf16 hi/lo operand) exist in the cluster kernel for single-item threads only
+  const bool extras = v2 && extras_done != nullptr && Bd * 2 <= 128 && dgsum != nullptr && dg_hi != nullptr && dg_lo != nullptr;
+  a.dgsum = extras ? dgsum : nullptr;
+  a.dg_hi = extras ? (__nv_bfloat16*)dg_hi : nullptr;
+  a.dg_lo = extras ? (__nv_bfloat16*)dg_lo : nullptr;
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   if (s->KPb != 4 * s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPb * 2, st));
   TMaps tm;
@@ -1379,18 +1411,19 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
     bool launched = false;
     if (v2cs == 8) {
       LV_TRY((v2_launch<false, 8>(s, a, tm, smem, st, &launched)));
-      if (launched) return LAGVAE_OK;
+      if (launched) { if (extras) *extras_done = true; return LAGVAE_OK; }
       cs_ok = 4;
       if (v2_geometry<false, 4>(s, Bd, &a, &smem)) {
         LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
         LV_TRY((v2_launch<false, 4>(s, a, tm, smem, st, &launched)));
-        if (launched) return LAGVAE_OK;
+        if (launched) { if (extras) *extras_done = true; return LAGVAE_OK; }
       }
     } else {
       LV_TRY((v2_launch<false, 4>(s, a, tm, smem, st, &launched)));
-      if (launched) return LAGVAE_OK;
+      if (launched) { if (extras) *extras_done = true; return LAGVAE_OK; }
     }
     cs_ok = 0;
+    a.dgsum = nullptr; a.dg_hi = a.dg_lo = nullptr;
     a.KP = s->KPb; a.KB = s->KPb / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
     LV_CHECK_ARG(ring_geometry(s->wb, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_backward: no ring geometry");

@@ -19,6 +19,9 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
                     cudaStream_t st);
 int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
                      const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
-                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st);
+                     float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st,
+                     // optional in-kernel extras (cluster kernel, Bd <= 64): dgsum [Bd,4nh] = sum over time of dG; dg_hi / dg_lo
+                     // [Tn*Bd,4nh] = dG as the bf16 hi/lo GEMM operand; *extras_done tells whether they were produced
+                     float* dgsum = nullptr, uint16_t* dg_hi = nullptr, uint16_t* dg_lo = nullptr, bool* extras_done = nullptr);
 
 }  // namespace lagvae

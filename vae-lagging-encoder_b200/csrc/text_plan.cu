@@ -705,16 +705,24 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   P->arena_off = P->arena_floor;  // dlogits staging no longer needed (unless the side stream still reads it)
 
   // ---- decoder LSTM backward (cuDNN RNN backward in the reference)
+  // the cluster recurrence kernel also emits Σ_t dG (-> dzb) and dG as the bf16 hi/lo operand of the weight-gradient GEMMs
+  static const bool no_extras = [] { const char* e = getenv("LAGVAE_LSTM_NO_EXTRAS"); return e && e[0] == '1'; }();
+  Staged sdg_k = P->lstm_tc && P->use_tc && !no_extras ? stage_alloc(P, rd, 4 * nh, &status) : Staged{};
+  LV_TRY(status);
+  bool extras = false;
   if (P->lstm_tc)
     LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc, P->dh_rec,
-                            P->dgates_d, Td, Bd, true, st));
+                            P->dgates_d, Td, Bd, true, st, P->dzb, const_cast<uint16_t*>(sdg_k.tc.hi),
+                            const_cast<uint16_t*>(sdg_k.tc.lo), &extras));
   else
     LV_TRY(lstm_backward_steps(w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc,
                                P->dh_rec, P->dgates_d, Td, Bd, nh, true, st));
-  LV_TRY(time_sum(P->dgates_d, Td, Bd, 4 * nh, P->dzb, st));
+  if (!extras) LV_TRY(time_sum(P->dgates_d, Td, Bd, 4 * nh, P->dzb, st));
   LV_TRY(col_sum(P->dzb, Bd, 4 * nh, gr->p[D_BIH], gr->p[D_BHH], st));
   {
-    Staged sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
+    Staged sdg = sdg_k;
+    sdg.m = Mat{P->dgates_d, rd, 4 * nh, 4 * nh};
+    if (!extras) sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
     Staged sxd = P->st_xd.tc.hi ? P->st_xd : stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
     // h_d itself (not its dropped-out version) pairs with dG in dW_hh: forward's copy serves only when dropout_out is off
     Staged shd = (P->st_h.tc.hi && !dout.mode) ? P->st_h : stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
@@ -765,16 +773,22 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
 
   // ---- encoder LSTM backward
   P->arena_off = P->fwd_arena_end;
+  Staged sdg_ke = P->lstm_tc && P->use_tc && !no_extras ? stage_alloc(P, re, 4 * nh, &status) : Staged{};
+  LV_TRY(status);
+  bool extras_e = false;
   if (P->lstm_tc)
     LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
-                            P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, false, st));
+                            P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, false, st, P->dzb, const_cast<uint16_t*>(sdg_ke.tc.hi),
+                            const_cast<uint16_t*>(sdg_ke.tc.lo), &extras_e));
   else
     LV_TRY(lstm_backward_steps(w->p[E_WHH], nullptr, P->gates_e, P->c_e, nullptr, spec_none(), P->dh_last,
                                P->dc_e, P->dh_rec_e, P->dgates_e, Te, B, nh, false, st));
-  LV_TRY(time_sum(P->dgates_e, Te, B, 4 * nh, P->dzb, st));   // Σ_t first (131 K threads), then Σ_b over B rows
+  if (!extras_e) LV_TRY(time_sum(P->dgates_e, Te, B, 4 * nh, P->dzb, st));   // Σ_t first (131 K threads), then Σ_b over B rows
   LV_TRY(col_sum(P->dzb, B, 4 * nh, gr->p[E_BIH], gr->p[E_BHH], st));
   {
-    Staged sdg = stage(P, Mat{P->dgates_e, re, 4 * nh, 4 * nh}, st, &status);
+    Staged sdg = sdg_ke;
+    sdg.m = Mat{P->dgates_e, re, 4 * nh, 4 * nh};
+    if (!extras_e) sdg = stage(P, Mat{P->dgates_e, re, 4 * nh, 4 * nh}, st, &status);
     Staged sxe = P->st_xe.tc.hi ? P->st_xe : stage(P, Mat{P->xe, re, ni, ni}, st, &status);
     Staged she = stage(P, Mat{P->h_e, re, nh, nh}, st, &status);
     Staged swx = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
