@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-for cs in 2 4; do for n in 2 4; do echo "== fwd cs $cs bulk $n"; LAGVAE_LSTM_FWD_CS=$cs LAGVAE_LSTM_BULK_STAGES=$n python scripts/lstm_trace.py > gpurun_out/trace_cs${cs}_b$n.log 2>&1; grep -E "forward kernel:|first stage|MMAs issued|accumulators|partials|cluster barrier|cell done|next step" gpurun_out/trace_cs${cs}_b$n.log | head -8; done; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_benchmarked_config.py -x -q -m gpu -k "lstm" > gpurun_out/pytest_lstm_quick.log 2>&1; tail -2 gpurun_out/pytest_lstm_quick.log
+python scripts/lstm_trace.py > gpurun_out/trace.log 2>&1; grep -E "kernel:|first stage|MMAs issued|accumulators|cell done|next step" gpurun_out/trace.log

@@ -63,6 +63,8 @@ struct RecArgs {
   __nv_bfloat16* dg_hi;          // backward, optional: dG as the bf16 hi / lo tensor-core operand [Tn*Bd, 4nh] of the weight-gradient
   __nv_bfloat16* dg_lo;          // GEMMs, written next to the fp32 copy — replaces a k_split_bf16 pass over dgates
   int bulk_stages;               // v2: ring stages per cp.async.bulk copy (LAGVAE_LSTM_BULK_STAGES, default 4)
+  int grouped;                   // v2: NS and the stages per step are multiples of bulk_stages -> the group partition is the same in
+                                 // every step and only the group LEADERS' barriers are used (one commit / wait per group)
   int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
 };
 
@@ -747,7 +749,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
       {
         PipeState q = ps;
         for (int j = 0; j < npre; ++j) {
-          ptx::mbar_wait(sm.empty(q.stage, a.NS), q.phase ^ 1u);
+          if (!a.grouped || (j % a.bulk_stages) == 0) ptx::mbar_wait(sm.empty(q.stage, a.NS), q.phase ^ 1u);
           if (++q.stage == a.NS) { q.stage = 0; q.phase ^= 1u; }
         }
       }
@@ -777,12 +779,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
         for (int i = 0; i < nst;) {
           const int glen = min(min(a.bulk_stages, nst - i), a.NS - ps.stage);     // contiguous in the ring, too
           for (int j = 0; j < glen; ++j)
-            if (i + j >= npre) ptx::mbar_wait(sm.empty(ps.stage + j, a.NS), ps.phase ^ 1u);   // slot re-used within the step
+            if (i + j >= npre && (!a.grouped || j == 0))
+              ptx::mbar_wait(sm.empty(ps.stage + j, a.NS), ps.phase ^ 1u);   // slot re-used within the step
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(sm.full(ps.stage), (uint32_t)glen * stage_bytes);
             bulk_g2s(sm.a_base + (uint32_t)ps.stage * stage_bytes, gsrc + (size_t)i * stage_bytes, (uint32_t)glen * stage_bytes,
                      sm.full(ps.stage));
-            for (int j = 1; j < glen; ++j) ptx::mbar_arrive(sm.full(ps.stage + j));
+            if (!a.grouped)
+              for (int j = 1; j < glen; ++j) ptx::mbar_arrive(sm.full(ps.stage + j));
           }
           __syncwarp();
           i += glen;
@@ -828,8 +832,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
             }
             kb = i / a.m_tiles;
             mt = i - kb * a.m_tiles;
+            // tcgen05.commit goes through the tensor pipe's queue like an MMA (~70 cycles each, measured): one per GROUP when
+            // the partition is step-invariant (only the leaders' barriers are then ever waited on), else one per stage
             for (int j = 0; j < glen; ++j) {
-              ptx::umma_commit(sm.empty(ps.stage + j, a.NS));
+              if (!a.grouped || j == 0) ptx::umma_commit(sm.empty(ps.stage + j, a.NS));
               if (kb == KBS - 1) ptx::umma_commit(sm.acc(mt, a.NS));
               if (++mt == a.m_tiles) { mt = 0; ++kb; }
             }
@@ -1234,6 +1240,10 @@ static bool v2_geometry(const LstmTcState* s, int Bd, RecArgs* a, size_t* smem) 
   // the loaders keep a group of stages in registers (16 chunks of 16 B per thread = floor(16 / (stage / 2 KB)) stages) and
   // store it before arriving on any of its barriers: the ring must hold a whole group
 
+  const int bulk = bulk_stages_env();
+  const int nst_step = KBS * m_tiles;
+  if (n >= bulk && nst_step % bulk == 0) n -= n % bulk;      // step-invariant group partition (see RecArgs::grouped)
+  a->grouped = (n % bulk == 0 && nst_step % bulk == 0) ? 1 : 0;
   a->part_bytes = rows_alloc * 128;
   a->NS = (int)n;
   a->KP = K;
