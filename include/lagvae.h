@@ -33,7 +33,7 @@ extern "C" {
 #define LAGVAE_E_CUDA 2    /* CUDA runtime / launch failure, or no usable sm_100 device */
 #define LAGVAE_E_WORKSPACE 3
 
-#define LAGVAE_ABI_VERSION 1
+#define LAGVAE_ABI_VERSION 2
 
 int lagvae_abi_version(void);
 const char* lagvae_last_error(void);
@@ -65,13 +65,17 @@ typedef struct lagvae_text_params {
 /* Dropout control (dec_lstm.py:30-31,81,106).  mode 0: identity (eval()).  mode 1: caller-provided
  * keep masks (uint8, 1 = keep): mask_in [B,Td,ni] (applied before the ns expansion, dec_lstm.py:81
  * precedes :87), mask_out [Bd,Td,nh].  mode 2: in-kernel counter-based Philox4x32-10 keyed by
- * (seed, stream id), element index = logical index in the shapes above. */
+ * (seed, stream id), element index = logical index in the shapes above.  seed_dev (mode 2, may be NULL): a device
+ * word ADDED to `seed` (mod 2^64) when the kernels run — a step captured in a CUDA graph freezes the host scalar `seed`,
+ * and draws a fresh mask at every replay by bumping that word inside the graph (the forward and the backward of one step
+ * must see the same value). */
 typedef struct lagvae_dropout {
   int32_t mode;
   float p_in, p_out;
   const uint8_t* mask_in;
   const uint8_t* mask_out;
   uint64_t seed;
+  const uint64_t* seed_dev;
 } lagvae_dropout;
 
 /* Opaque per-shape plan: workspace carving + kernel selection. */

@@ -621,6 +621,113 @@ int ce_bwd_split(const float* logits, int64_t ld, int V, const int64_t* x, int64
   return LAGVAE_OK;
 }
 
+// Forward AND backward of the cross entropy in one pass over the logits, for callers that know the upstream gradient of
+// every reconstruction row before the forward runs (the fused steps: text.py:382 / :413 take mean(dim=-1), so it is 1/B):
+// the row (V fp32 = 80 KB at Yahoo's V) is held in registers between the log-sum-exp and the (softmax - onehot)·g
+// emission, so the 509 MB logits tensor is read from HBM once instead of twice.  One 512-thread block per (t, bd) row,
+// NV4 float4 per thread (V <= 2048·NV4).
+template <int NV4>
+__global__ void __launch_bounds__(512)
+k_ce_fused(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ x, int64_t x_ld, int Bd, int ns,
+           float g, float* __restrict__ lse_out, float* __restrict__ loss_row, __nv_bfloat16* __restrict__ hi,
+           __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  __shared__ float red[16];
+  __shared__ float bcast[2];
+  const int row = blockIdx.x;
+  const int bd = row % Bd, t = row / Bd, b = bd / ns;
+  const float* l = logits + (int64_t)row * ld;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 r[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int v0 = (threadIdx.x + i * 512) * 4;
+    if (v0 + 3 < V) {
+      r[i] = *(const float4*)(l + v0);
+    } else {
+      r[i].x = (v0 + 0 < V) ? l[v0 + 0] : -INFINITY;
+      r[i].y = (v0 + 1 < V) ? l[v0 + 1] : -INFINITY;
+      r[i].z = (v0 + 2 < V) ? l[v0 + 2] : -INFINITY;
+      r[i].w = -INFINITY;
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) m = fmaxf(m, fmaxf(fmaxf(r[i].x, r[i].y), fmaxf(r[i].z, r[i].w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  if (w == 0) {
+    float v = (lane < 16) ? red[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) bcast[0] = v;
+  }
+  __syncthreads();
+  m = bcast[0];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (expf(r[i].x - m) + expf(r[i].y - m)) + (expf(r[i].z - m) + expf(r[i].w - m));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[w] = s;
+  __syncthreads();
+  const int64_t tgt = x[(int64_t)b * x_ld + 1 + t];   // tgt = x[:,1:]  dec_lstm.py:127
+  if (w == 0) {
+    float v = (lane < 16) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      const float L = m + logf(v);
+      bcast[1] = L;
+      lse_out[row] = L;
+      loss_row[row] = L - l[tgt];
+    }
+  }
+  __syncthreads();
+  const float L = bcast[1];
+  __nv_bfloat16* h = hi + (int64_t)row * ld_out;
+  __nv_bfloat16* c = lo + (int64_t)row * ld_out;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int v0 = (threadIdx.x + i * 512) * 4;
+    if (v0 < ld_out) {
+      const float xv[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+      __nv_bfloat16 a[4], e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d = 0.f;
+        if (v0 + j < V) {
+          float p = expf(xv[j] - L);
+          if (v0 + j == tgt) p -= 1.f;
+          d = p * g;
+        }
+        split_bf16(d, a[j], e[j]);
+      }
+      *(uint2*)(h + v0) = pack_bf16x4(a);
+      *(uint2*)(c + v0) = pack_bf16x4(e);
+    }
+  }
+}
+// returns LAGVAE_OK and sets *done when the shape is supported (otherwise the caller keeps the two-kernel path)
+int ce_fused(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd, int ns, float g_row,
+             float* lse_out, float* loss_row, uint16_t* hi, uint16_t* lo, int64_t ld_out, bool* done, cudaStream_t st) {
+  *done = false;
+  const bool vec = ((ld & 3) == 0) && ((((uintptr_t)logits) & 15) == 0) && ((ld_out & 3) == 0);
+  if (!vec || ld_out > 2048 * 10 || V < 1) return LAGVAE_OK;
+  auto* h = (__nv_bfloat16*)hi;
+  auto* c = (__nv_bfloat16*)lo;
+  if (ld_out <= 2048 * 3)
+    k_ce_fused<3><<<Tn * Bd, 512, 0, st>>>(logits, ld, V, x, x_ld, Bd, ns, g_row, lse_out, loss_row, h, c, ld_out);
+  else if (ld_out <= 2048 * 6)
+    k_ce_fused<6><<<Tn * Bd, 512, 0, st>>>(logits, ld, V, x, x_ld, Bd, ns, g_row, lse_out, loss_row, h, c, ld_out);
+  else
+    k_ce_fused<10><<<Tn * Bd, 512, 0, st>>>(logits, ld, V, x, x_ld, Bd, ns, g_row, lse_out, loss_row, h, c, ld_out);
+  LV_LAUNCH_CHECK();
+  *done = true;
+  return LAGVAE_OK;
+}
+
 // rec[b] = mean_s Σ_t loss_row ; loss[b] = rec + klw*KL   (dec_lstm.py:148, vae.py:95,98);
 // scalars[0..2] = Σloss, Σrec, ΣKL (text.py:381 reads Σloss).  Single block.
 __global__ void __launch_bounds__(256)

@@ -122,11 +122,13 @@ struct DropSpec {  // resolved view of lagvae_dropout for one of the two masks
   const uint8_t* mask;
   uint64_t seed;
   uint32_t sid;
+  const uint64_t* seed_dev;   // optional device word added to `seed` at run time (graph replays), lagvae.h
 };
 __device__ __forceinline__ float drop_factor(const DropSpec& d, uint64_t idx) {
   if (d.mode == 0) return 1.0f;
   if (d.mode == 1) return d.mask[idx] ? d.scale : 0.0f;
-  return philox_keep(d.seed, d.sid, idx, d.p) ? d.scale : 0.0f;
+  const uint64_t key = d.seed_dev ? d.seed + __ldg((const unsigned long long*)d.seed_dev) : d.seed;
+  return philox_keep(key, d.sid, idx, d.p) ? d.scale : 0.0f;
 }
 
 // ---- internal launchers shared between translation units --------------------------------------

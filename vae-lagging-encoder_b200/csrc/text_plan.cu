@@ -67,6 +67,11 @@ struct lagvae_text_plan {
   lagvae_dropout drop;
   float kl_weight;
   bool have_forward;
+  // fused steps only: the upstream gradient of every reconstruction row is known before the forward runs (> 0), so the
+  // forward's cross-entropy pass also emits dlogits as the split-bf16 operand of the backward GEMMs (st_dl)
+  float ce_upstream;
+  Staged st_dl;
+  bool dl_ready;
   int dec_wgrad_passes;  // 3 = fp32-grade; 1 = single bf16 pass (fused inner step: these gradients only feed the clip norm)
 };
 
@@ -175,8 +180,9 @@ void carve(lagvae_text_plan* P, char* base) {
 void reset_pass(lagvae_text_plan* P) {
   P->arena_off = 0;
   P->fwd_arena_end = 0;
-  P->st_xe = P->st_xd = P->st_h = Staged{Mat{nullptr, 0, 0, 0}, TcOperand{nullptr, nullptr, 0, 0}};
+  P->st_xe = P->st_xd = P->st_h = P->st_dl = Staged{Mat{nullptr, 0, 0, 0}, TcOperand{nullptr, nullptr, 0, 0}};
   P->have_forward = false;
+  P->dl_ready = false;
 }
 
 bool dims_ok(const lagvae_text_dims* d) {
@@ -299,6 +305,7 @@ DropSpec spec_in(const lagvae_dropout& d) {
   s.scale = on ? 1.f / (1.f - d.p_in) : 1.f;
   s.mask = d.mask_in;
   s.seed = d.seed;
+  s.seed_dev = s.mode == 2 ? d.seed_dev : nullptr;
   s.sid = 1;
   return s;
 }
@@ -310,6 +317,7 @@ DropSpec spec_out(const lagvae_dropout& d) {
   s.scale = on ? 1.f / (1.f - d.p_out) : 1.f;
   s.mask = d.mask_out;
   s.seed = d.seed;
+  s.seed_dev = s.mode == 2 ? d.seed_dev : nullptr;
   s.sid = 2;
   return s;
 }
@@ -433,7 +441,22 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   Staged swp = stage_dec_weight(P, 1, Mat{w->p[D_PRED], V, nh, nh}, st, &status);
   LV_TRY(status);
   LV_TRY(mm(P, sh, false, swp, false, P->logits, P->ldl, (int)P->rd, V, nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
-  if (with_ce) LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
+  if (with_ce) {
+    static const bool fused_env = [] { const char* e = getenv("LAGVAE_FUSED_CE"); return !(e && e[0] == '0'); }();
+    bool done = false;
+    if (fused_env && P->ce_upstream > 0.f && P->use_tc && P->rd >= 32 && nh >= 16 && V >= 32) {
+      // same bump allocation the backward makes first (arena_off == fwd_arena_end here), so it finds the operand in place
+      Staged sdl = stage_alloc(P, P->rd, V, &status);
+      LV_TRY(status);
+      LV_TRY(ce_fused(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->ce_upstream / (float)ns, P->lse, P->loss_row,
+                      const_cast<uint16_t*>(sdl.tc.hi), const_cast<uint16_t*>(sdl.tc.lo), sdl.tc.ld, &done, st));
+      if (done) {
+        P->st_dl = sdl;
+        P->dl_ready = true;
+      }
+    }
+    if (!done) LV_TRY(ce_fwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->loss_row, st));
+  }
   return LAGVAE_OK;
 }
 
@@ -519,6 +542,8 @@ int lagvae_text_plan_create(const lagvae_text_dims* d, uint32_t flags, void* wor
     return r;
   }
   P->have_forward = false;
+  P->ce_upstream = 0.f;
+  P->dl_ready = false;
   P->dec_wgrad_passes = 3;
   P->dec_epoch = 0;
   P->wc = wcache_state_for(workspace);
@@ -669,8 +694,12 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     if (tc_dl) {
       sdl = stage_alloc(P, rd, V, &status);
       LV_TRY(status);
-      LV_TRY(ce_bwd_split(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, const_cast<uint16_t*>(sdl.tc.hi),
-                          const_cast<uint16_t*>(sdl.tc.lo), sdl.tc.ld, st));
+      // fused steps: the forward's cross-entropy pass already wrote it (same allocation, upstream known in advance)
+      const bool have_dl = P->dl_ready && P->st_dl.tc.hi == sdl.tc.hi && P->st_dl.tc.lo == sdl.tc.lo;
+      P->dl_ready = false;
+      if (!have_dl)
+        LV_TRY(ce_bwd_split(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, const_cast<uint16_t*>(sdl.tc.hi),
+                            const_cast<uint16_t*>(sdl.tc.lo), sdl.tc.ld, st));
     } else {
       LV_TRY(ce_bwd(P->logits, P->ldl, V, x, d.T, Td, Bd, ns, P->lse, P->g_rec, st));
       sdl = stage(P, Mat{P->logits, rd, V, P->ldl}, st, &status);
@@ -836,8 +865,11 @@ static int text_step(lagvae_text_plan* P, const lagvae_text_params* w, const int
     off += counts[i];
   }
   // text.py:379 / :411 loss; :381 Σloss; :382 / :413 mean(dim=-1) -> upstream 1/B
-  LV_TRY(lagvae_text_loss_forward(P, w, x, eps, kl_weight, drop, out_loss, P->dml /*rec tmp*/, P->dh_last /*kl tmp*/,
-                                  nullptr, nullptr, nullptr, stream));
+  P->ce_upstream = 1.f / (float)d.B;
+  const int rf = lagvae_text_loss_forward(P, w, x, eps, kl_weight, drop, out_loss, P->dml /*rec tmp*/, P->dh_last /*kl tmp*/,
+                                          nullptr, nullptr, nullptr, stream);
+  P->ce_upstream = 0.f;
+  LV_TRY(rf);
   LV_CUDA(cudaMemcpyAsync(out_scalars, P->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   LV_TRY(fill(P->dc0t, 1.f / (float)d.B, d.B, st));
   // Decoder WEIGHT gradients that are not applied (aggressive inner loop: text.py:387 steps the encoder only) enter the

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblagvae.so")
 
 OK, E_ARG, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 NPARAM = 13
 PLAN_DEFAULT, PLAN_FORCE_SIMT, PLAN_INFERENCE = 0, 1, 2
 BWD_DEFAULT, BWD_DECODER_WGRAD_NORM_ONLY = 0, 1
@@ -45,7 +45,7 @@ class PixelBlockGrads(C.Structure):
 
 class Dropout(C.Structure):
     _fields_ = [("mode", C.c_int32), ("p_in", C.c_float), ("p_out", C.c_float),
-                ("mask_in", C.c_void_p), ("mask_out", C.c_void_p), ("seed", C.c_uint64)]
+                ("mask_in", C.c_void_p), ("mask_out", C.c_void_p), ("seed", C.c_uint64), ("seed_dev", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/lagvae.h (tests check this)

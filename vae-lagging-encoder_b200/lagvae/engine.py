@@ -9,6 +9,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _backend as be
+from . import graph as graph_mod
 
 PARAM_NAMES = [
     "encoder.embed.weight", "encoder.lstm.weight_ih_l0", "encoder.lstm.weight_hh_l0",
@@ -22,19 +23,22 @@ N_ENC = 6
 
 @dataclass
 class DropoutSpec:
-    """mode 0 = off (eval), 1 = explicit uint8 keep-masks, 2 = in-kernel Philox (include/lagvae.h)."""
+    """mode 0 = off (eval), 1 = explicit uint8 keep-masks, 2 = in-kernel Philox (include/lagvae.h).  seed_dev: optional
+    int64 device tensor [1] added to `seed` when the kernels run (CUDA-graph replays bump it, lagvae/graph.py)."""
     mode: int = 0
     p_in: float = 0.0
     p_out: float = 0.0
     mask_in: Optional[torch.Tensor] = None   # uint8 [B, T-1, ni]
     mask_out: Optional[torch.Tensor] = None  # uint8 [B*ns, T-1, nh]
     seed: int = 0
+    seed_dev: Optional[torch.Tensor] = None
 
     def to_c(self):
         d = be.Dropout()
         d.mode, d.p_in, d.p_out, d.seed = int(self.mode), float(self.p_in), float(self.p_out), int(self.seed) & (2 ** 64 - 1)
         d.mask_in = self.mask_in.data_ptr() if self.mask_in is not None else None
         d.mask_out = self.mask_out.data_ptr() if self.mask_out is not None else None
+        d.seed_dev = self.seed_dev.data_ptr() if self.seed_dev is not None else None
         return d
 
 
@@ -141,8 +145,13 @@ class TextEngine:
         7 decoder tensors — every in-place update (optimizer step, load_state_dict, copy_) bumps a counter — plus a counter
         for the updates liblagvae.so makes itself (outer_step), which torch cannot see."""
         dec = params[N_ENC:]
-        if any(t is None for t in dec):
-            epoch = 0
+        capturing = torch.cuda.is_current_stream_capturing()
+        serial = graph_mod.capture_serial() if capturing else None
+        if any(t is None for t in dec) or (capturing and serial is None):
+            epoch = 0        # bare torch.cuda.graph: the decision below would be frozen into the graph -> never cache
+        elif capturing:
+            # one epoch per GraphedStep capture: the first captured step re-splits at every replay, the rest reuse (graph.py)
+            epoch = ((serial * 2654435761 + self._uid * 998244353 + 0x5bd1e995) & (2 ** 63 - 1)) | 1
         else:
             # engine uid + workspace generation: a NEW engine / workspace must never hit a cache entry that an earlier one
             # left behind at a recycled address (the allocator hands freed workspaces and tensors out again)

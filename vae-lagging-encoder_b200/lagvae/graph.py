@@ -13,9 +13,14 @@ Two more, specific to this library:
 * a captured graph holds RAW device pointers into the engine workspace / the image scratch buffers.  Those buffers grow on
   demand (a larger eager call later, e.g. `nll_iw` on B*ns rows); while any GraphedStep is alive a buffer that is outgrown is
   RETIRED (kept allocated, `retire()` below) instead of freed, so a replay never writes freed memory;
-* host scalars are frozen at capture.  That includes the Philox dropout seed of the text decoder: capturing a text model in
-  train() mode with in-kernel dropout would replay ONE mask for ever, so `modules.text.dropout_spec` refuses to build a Philox
-  spec while a stream is capturing (use eval(), p = 0, or LAGVAE_DROPOUT=torch masks drawn outside the graph)."""
+* host scalars are frozen at capture.  The Philox dropout seed of the text decoder is one: a captured train()-mode step
+  therefore keys its masks by `seed + *seed_dev` (include/lagvae.h, lagvae_dropout.seed_dev) — `philox_word(device)` is
+  that device word and `bump_philox_word` advances it INSIDE the graph by the same constant an eager call advances the host
+  seed by, so replay k draws exactly the masks of the k-th eager call (tests/test_gpu_text_graph.py);
+* the decoder-weight operand cache (lagvae_text_decoder_weights_epoch) is decided on the host, i.e. at capture: inside a
+  GraphedStep capture the engine declares one epoch per capture (`capture_serial()`), so the FIRST captured step re-splits
+  the decoder weights at every replay and the following steps of the same graph reuse them (a 15-step window of
+  text.py:371-400 splits once); under a bare torch.cuda.graph the cache is off (epoch 0)."""
 import weakref
 from typing import Callable, Dict, Sequence, Union
 
@@ -23,6 +28,29 @@ import torch
 
 _LIVE = weakref.WeakSet()      # GraphedStep objects that are alive
 _RETIRED = []                  # outgrown buffers kept allocated while a graph may still reference them
+_SERIAL = [0, False]           # [captures started so far, a GraphedStep capture is in progress]
+_WORDS = {}                    # device index -> int64 [1] Philox offset word
+PHILOX_STEP = 0xD1B54A32D192ED03   # what one eager decoder forward adds to the host seed (modules/text.py::dropout_spec)
+
+
+def capture_serial():
+    """Non-zero and constant while ONE GraphedStep capture is in progress, None otherwise."""
+    return _SERIAL[0] if _SERIAL[1] else None
+
+
+def philox_word(device):
+    """The device word a captured step adds to its (frozen) Philox seed; one per device, shared by all graphs."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _WORDS:
+        _WORDS[idx] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+    return _WORDS[idx]
+
+
+def bump_philox_word(word, times=1):
+    """Enqueue word += times * PHILOX_STEP (mod 2^64) on the current stream — call it inside the captured body, before the
+    forward that uses the word."""
+    inc = (PHILOX_STEP * int(times)) & (2 ** 64 - 1)
+    word.add_(inc - 2 ** 64 if inc >= 2 ** 63 else inc)
 
 
 def retire(t):
@@ -49,8 +77,13 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            out = body(**self.static_in)
+        _SERIAL[0] += 1
+        _SERIAL[1] = True
+        try:
+            with torch.cuda.graph(self.graph):
+                out = body(**self.static_in)
+        finally:
+            _SERIAL[1] = False
         self._single = isinstance(out, torch.Tensor)
         self.static_out = [out] if self._single else list(out)
         _LIVE.add(self)

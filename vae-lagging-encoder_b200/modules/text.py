@@ -14,6 +14,7 @@ import torch.nn as nn
 
 from lagvae import DropoutSpec, LagvaeError, TextEngine
 from lagvae import _backend as be
+from lagvae import graph as _graph
 
 _ENGINES = {}
 _CALLS = [0]
@@ -61,10 +62,14 @@ def dropout_spec(dec, B, T, ns, device, row_offset=0, rows_total=None):
         m_out = (torch.rand(total * ns, T - 1, dec.nh, device=device) >= p_out).to(torch.uint8)[lo * ns:hi * ns].contiguous() if p_out > 0 else None
         return DropoutSpec(1, p_in, p_out, m_in, m_out, 0)
     if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
-        raise LagvaeError("in-kernel (Philox) dropout cannot be captured in a CUDA graph: the seed is a host scalar and every "
-                          "replay would reuse one mask (lagvae/graph.py); use eval(), p = 0 or LAGVAE_DROPOUT=torch")
+        # the host seed is frozen into the graph: key the masks by seed + a device word that the graph itself advances by
+        # the step an eager call advances _CALLS by — replay k then draws the masks of the k-th eager call (lagvae/graph.py)
+        word = _graph.philox_word(device)
+        _graph.bump_philox_word(word)
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * _graph.PHILOX_STEP + int(row_offset) * 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
+        return DropoutSpec(2, p_in, p_out, None, None, seed, word)
     _CALLS[0] += 1
-    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * 0xD1B54A32D192ED03 + int(row_offset) * 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _CALLS[0] * _graph.PHILOX_STEP + int(row_offset) * 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
     return DropoutSpec(2, p_in, p_out, None, None, seed)
 
 
