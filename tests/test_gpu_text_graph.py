@@ -96,10 +96,12 @@ def test_graphed_window_of_fused_inner_steps_equals_eager(shape):
         torch.cuda.synchronize()
         for i in range(W):
             k = wdw * W + i
-            assert torch.allclose(l[i], want_loss[k], rtol=1e-5, atol=1e-5), (k, (l[i] - want_loss[k]).abs().max())
-            assert torch.allclose(s[i], want_sc[k], rtol=1e-5, atol=1e-6), (k, s[i], want_sc[k])
+            # same kernels in the same order; what differs is the summation order of the atomics (embedding scatter-add,
+            # split-K), amplified step by step through the lr-1.0 updates: 1e-4, against O(1) for a wrong mask or weight
+            assert torch.allclose(l[i], want_loss[k], rtol=1e-4, atol=1e-4), (k, (l[i] - want_loss[k]).abs().max())
+            assert torch.allclose(s[i], want_sc[k], rtol=1e-4, atol=1e-5), (k, s[i], want_sc[k])
     for a, b in zip(pg, pe):
-        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+        assert float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-6)
     # fresh masks per step: two steps on different masks cannot produce the same reconstruction sum
     assert float(want_sc[0][1]) != float(want_sc[1][1])
     if nh >= 256 and B <= 32:

@@ -371,7 +371,10 @@ int lstm_backward_steps(const float* w_hh, const float* c0, const float* gates, 
   return LAGVAE_OK;
 }
 
-int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, cudaStream_t st) {
+// fork (optional): recorded on `st` right before the recurrence is launched, i.e. after the input-projection GEMM — work
+// that a side stream runs behind it overlaps the recurrence and nothing else
+int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, cudaStream_t st,
+                    cudaEvent_t fork = nullptr) {
   const lagvae_text_dims& d = P->d;
   const int nh = d.nh, ni = d.ni;
   int status = LAGVAE_OK;
@@ -387,6 +390,7 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
             0, 3, st));
   P->arena_off = keep;                            // the W_ih copy is dead once the GEMM is enqueued (stream order)
   P->fwd_arena_end = keep;
+  if (fork) LV_CUDA(cudaEventRecord(fork, st));
   if (P->lstm_tc)
     LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[E_WHH], nullptr, nullptr, P->gates_e, P->c_e, P->h_e, nullptr, spec_none(),
                            P->Te, d.B, st));
@@ -400,15 +404,45 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
 // decoder forward up to per-token CE (dec_lstm.py:66-148).  z: device [Bd, nz].
 // x_ld: row stride of the token tensor (d.T for the [B,T] training batches, T-1 for LSTMDecoder.decode's `input`);
 // with_ce = false stops after the vocabulary projection (targets are not read).
+// The z-independent front of the decoder forward: embedding + input dropout (dec_lstm.py:80-81, 87-91) and the x-columns of
+// the input projection (first half of nn.LSTM, :104).  Returns whether the tensor-core GEMM ran (then the row-periodic z
+// bias is still to be added).  `cap` > 0 limits the GEMM grid (side stream under a persistent recurrence).
+int decoder_xproj(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, const lagvae_dropout& dr,
+                  cudaStream_t st, int64_t x_ld, int cap, bool* ran_tc) {
+  const lagvae_text_dims& d = P->d;
+  const int nh = d.nh, ni = d.ni, nz = d.nz, B = d.B, ns = d.ns, Td = P->Td;
+  int status = LAGVAE_OK;
+  *ran_tc = false;
+  LV_TRY(embed_gather(x, x_ld, 0, B, ns, Td, w->p[D_EMB], ni, spec_in(dr), P->xd, st));       // :80-81 (+:87-91)
+  Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
+  P->st_xd = sxd;
+  Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
+  LV_TRY(status);
+  if (P->use_tc && sxd.tc.hi && swd.tc.hi) {
+    gemm_tc_set_grid_cap(cap);
+    const int r = mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, nullptr, 0, 3, st);
+    gemm_tc_set_grid_cap(0);
+    LV_TRY(r);
+    *ran_tc = true;
+  }
+  return LAGVAE_OK;
+}
+
+// xproj_state: 0 = run the front here; 1 = decoder_xproj already ran (tensor-core GEMM done, bias pending); 2 = it ran but
+// fell to the non-tensor-core tier (GEMM + bias still to do here)
 int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int64_t* x, const float* z,
-                    const lagvae_dropout& dr, cudaStream_t st, int64_t x_ld = -1, bool with_ce = true) {
+                    const lagvae_dropout& dr, cudaStream_t st, int64_t x_ld = -1, bool with_ce = true, int xproj_state = 0) {
   const lagvae_text_dims& d = P->d;
   const int nh = d.nh, ni = d.ni, nz = d.nz, V = d.V, B = d.B, ns = d.ns, Bd = P->Bd, Td = P->Td;
   int status = LAGVAE_OK;
   // ---- decoder: dec_lstm.py:66-111
-  const DropSpec din = spec_in(dr), dout = spec_out(dr);
+  const DropSpec dout = spec_out(dr);
   if (x_ld < 0) x_ld = d.T;
-  LV_TRY(embed_gather(x, x_ld, 0, B, ns, Td, w->p[D_EMB], ni, din, P->xd, st));               // :80-81 (+:87-91)
+  if (xproj_state == 0) {
+    bool ran = false;
+    LV_TRY(decoder_xproj(P, w, x, dr, st, x_ld, 0, &ran));
+    xproj_state = ran ? 1 : 2;
+  }
   LV_TRY(vec_add(w->p[D_BIH], w->p[D_BHH], P->bsum_d, 4 * nh, st));
   // z enters every step through the last nz input columns (:84,97): time-invariant row bias
   LV_TRY(gemm_f32(z, nz, 1, w->p[D_WIH] + ni, ni + nz, 1, P->zb, 4 * nh, Bd, 4 * nh, nz, 1.f, 0.f,
@@ -416,16 +450,13 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   LV_TRY(gemm_f32(z, nz, 1, w->p[D_TRANS], nz, 1, P->c0, nh, Bd, nh, nz, 1.f, 0.f, nullptr, nullptr, 0,
                   st));                                                                      // :100
   LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
-  Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
-  P->st_xd = sxd;
-  Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
-  LV_TRY(status);
-  if (P->use_tc && sxd.tc.hi && swd.tc.hi) {
-    // tensor-core tier: plain GEMM, then the row-periodic z bias in one streaming pass (see k_add_row_periodic)
-    LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+  if (xproj_state == 1) {
+    // tensor-core tier: plain GEMM (decoder_xproj), then the row-periodic z bias in one streaming pass (see k_add_row_periodic)
     LV_TRY(add_row_periodic(P->gates_d, P->zb, P->rd, 4 * nh, Bd, st));
   } else {
-    LV_TRY(mm(P, sxd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
+    Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
+    LV_TRY(status);
+    LV_TRY(mm(P, P->st_xd, false, swd, false, P->gates_d, 4 * nh, (int)P->rd, 4 * nh, ni, 1.f, 0.f, nullptr, P->zb, Bd,
               3, st));
   }
   float* hdrop = dout.mode ? P->hdrop_d : nullptr;
@@ -619,12 +650,34 @@ int lagvae_text_loss_forward(lagvae_text_plan* P, const lagvae_text_params* w, c
   int status = LAGVAE_OK;
 
   // ---- encoder: enc_lstm.py:47-64 ; reparameterise + KL: encoder.py:40-79
-  LV_TRY(encoder_forward(P, w, x, st));
+  // The decoder's embedding + x-projection do not depend on z: they run on a side stream UNDER the encoder recurrence, on
+  // the 20 SMs its 128 persistent CTAs leave idle (GEMM grid capped to them; scripts/microbench/overlap_probe.py: the
+  // forward recurrence and a 20-CTA GEMM overlap fully in both launch orders).  LAGVAE_OVERLAP_XPROJ=0 turns it off.
+  static const bool ov_env = [] { const char* e = getenv("LAGVAE_OVERLAP_XPROJ"); return !(e && e[0] == '0'); }();
+  const bool overlap = ov_env && P->use_tc && P->lstm_tc && nh >= 256 && B <= 128 && P->rd >= 128;
+  int xstate = 0;
+  if (overlap) {
+    if (!P->side) {
+      LV_CUDA(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+      LV_CUDA(cudaEventCreateWithFlags(&P->side_fork, cudaEventDisableTiming));
+      LV_CUDA(cudaEventCreateWithFlags(&P->side_join, cudaEventDisableTiming));
+    }
+    LV_TRY(encoder_forward(P, w, x, st, P->side_fork));
+    LV_CUDA(cudaStreamWaitEvent(P->side, P->side_fork, 0));
+    bool ran = false;
+    const int r = decoder_xproj(P, w, x, dr, P->side, d.T, 20, &ran);   // 148 SMs - 128 recurrence CTAs
+    LV_CUDA(cudaEventRecord(P->side_join, P->side));                     // joined even on error: no dangling fork
+    LV_CUDA(cudaStreamWaitEvent(st, P->side_join, 0));
+    LV_TRY(r);
+    xstate = ran ? 1 : 2;
+  } else {
+    LV_TRY(encoder_forward(P, w, x, st));
+  }
   LV_CUDA(cudaMemcpyAsync(P->eps, eps, sizeof(float) * Bd * nz, cudaMemcpyDeviceToDevice, st));
   const float* h_last = P->h_e + (int64_t)(P->Te - 1) * B * nh;
   LV_TRY(head_reparam_kl(h_last, w->p[E_LIN], P->eps, B, nh, nz, ns, P->mu, P->logvar, P->z, P->kl, st));
 
-  LV_TRY(decoder_forward(P, w, x, P->z, dr, st));
+  LV_TRY(decoder_forward(P, w, x, P->z, dr, st, -1, true, xstate));
   LV_TRY(finalize_loss(P->loss_row, P->kl, B, ns, Td, kl_weight, out_loss, out_rec, out_kl, P->scalars, st));
   if (out_mu) LV_CUDA(cudaMemcpyAsync(out_mu, P->mu, sizeof(float) * B * nz, cudaMemcpyDeviceToDevice, st));
   if (out_logvar)
