@@ -728,6 +728,19 @@ int ce_fused(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x
   return LAGVAE_OK;
 }
 
+// Side-stream gate: returns once *flag != 0 (set by a persistent kernel of another stream when its whole grid is resident),
+// consumes the flag, and gives up after max_cycles so that a launch that never sets it cannot hang the stream.
+__global__ void k_wait_flag(unsigned* flag, long long max_cycles) {
+  const long long t0 = clock64();
+  while (*(volatile unsigned*)flag == 0u && clock64() - t0 < max_cycles) __nanosleep(500);
+  *(volatile unsigned*)flag = 0u;
+}
+int wait_flag(unsigned* flag, long long max_cycles, cudaStream_t st) {
+  k_wait_flag<<<1, 1, 0, st>>>(flag, max_cycles);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
+
 // rec[b] = mean_s Σ_t loss_row ; loss[b] = rec + klw*KL   (dec_lstm.py:148, vae.py:95,98);
 // scalars[0..2] = Σloss, Σrec, ΣKL (text.py:381 reads Σloss).  Single block.
 __global__ void __launch_bounds__(256)

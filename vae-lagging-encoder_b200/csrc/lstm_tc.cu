@@ -66,6 +66,8 @@ struct RecArgs {
   int grouped;                   // v2: NS and the stages per step are multiples of bulk_stages -> the group partition is the same in
                                  // every step and only the group LEADERS' barriers are used (one commit / wait per group)
   int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
+  unsigned* started;             // optional: set to 1 once every CTA of the persistent grid is running (a side stream gates work on it
+                                 // so that it takes the SMs the clusters leave over and never the ones they need)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -681,6 +683,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
   ptx::fence_proxy_async_all();
   cluster_sync_all();                                // peers' smem (receive slots, barriers) exist before any DSMEM access
   grid_barrier(a.bar, gridDim.x);                    // epoch 1: initial operand published; step s ends epoch s + 2
+  if (a.started != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *(volatile unsigned*)a.started = 1u;
 
   PipeState ps{0, 0};      // ring position (producer warp and MMA warp each advance their own copy)
   const bool trace = a.dbg != nullptr && blockIdx.x == 0;
@@ -1383,7 +1386,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
 int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
                      const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
                      float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st, float* dgsum,
-                     uint16_t* dg_hi, uint16_t* dg_lo, bool* extras_done) {
+                     uint16_t* dg_hi, uint16_t* dg_lo, bool* extras_done, unsigned* started) {
   if (extras_done) *extras_done = false;
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_backward: bad arguments");
   LV_TRY(configure(s));
@@ -1410,6 +1413,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
   a.dh_rec_out = dh_rec; a.dgates = dgates; a.want_init = want_init ? 1 : 0;
   // the in-kernel extras (time sum of dG, dG as bf16 hi/lo operand) exist in the cluster kernel for single-item threads only
   const bool extras = v2 && extras_done != nullptr && Bd * 2 <= 128 && dgsum != nullptr && dg_hi != nullptr && dg_lo != nullptr;
+  a.started = v2 ? started : nullptr;
   a.dgsum = extras ? dgsum : nullptr;
   a.dg_hi = extras ? (__nv_bfloat16*)dg_hi : nullptr;
   a.dg_lo = extras ? (__nv_bfloat16*)dg_lo : nullptr;

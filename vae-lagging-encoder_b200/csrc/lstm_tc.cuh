@@ -22,6 +22,8 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
                      float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st,
                      // optional in-kernel extras (cluster kernel, Bd <= 64): dgsum [Bd,4nh] = sum over time of dG; dg_hi / dg_lo
                      // [Tn*Bd,4nh] = dG as the bf16 hi/lo GEMM operand; *extras_done tells whether they were produced
-                     float* dgsum = nullptr, uint16_t* dg_hi = nullptr, uint16_t* dg_lo = nullptr, bool* extras_done = nullptr);
+                     float* dgsum = nullptr, uint16_t* dg_hi = nullptr, uint16_t* dg_lo = nullptr, bool* extras_done = nullptr,
+                     // optional device word set to 1 by the cluster kernel once its whole grid is running
+                     unsigned* started = nullptr);
 
 }  // namespace lagvae

@@ -61,6 +61,7 @@ struct lagvae_text_plan {
   cudaStream_t side;
   cudaEvent_t side_fork, side_join;
   size_t arena_floor;    // staging below this offset is still read by the side stream
+  unsigned* side_gate;   // device word: set by the decoder backward recurrence once its grid is resident (wait_flag on `side`)
   // state carried from forward to backward
   Staged st_xe, st_xd, st_h;   // forward's bf16 hi/lo operand copies of xe, xd and hdrop/h_d: the backward GEMMs reuse them
   size_t fwd_arena_end;        // ... so the backward's bump allocation starts behind them
@@ -170,6 +171,7 @@ void carve(lagvae_text_plan* P, char* base) {
   P->dc_e = c.take<float>(B * nh);
   P->dh_rec_e = c.take<float>(B * nh);
   P->clip_scratch = c.take<char>(16384);
+  P->side_gate = c.take<unsigned>(64);
   P->arena_bytes = P->use_tc ? arena_need(d) : 0;
   P->arena = c.take<char>((int64_t)P->arena_bytes);
   c.off = (size_t)round_up((int64_t)c.off, 256);
@@ -729,12 +731,21 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   P->arena_off = P->fwd_arena_end;   // forward's copies of xe | xd | h stay alive below this offset
   P->arena_floor = P->fwd_arena_end;
   P->have_forward = false;  // logits are consumed in place
-  // norm-only dW_pred on a side stream under the decoder recurrence: OPT-IN (LAGVAE_SIDE_WGRAD=1).  Correct (the
-  // full-shape fused-step test passes with it), but measured SLOWER on the B200: 10.22 vs 9.49 ms/step — the 20 GEMM CTAs
-  // delay the co-residency of the backward recurrence's clusters of 4 (profiles/README.md, r1i); kept for the next round.
-  static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return e && e[0] == '1'; }();
-  const bool side_wgrad = side_env && P->use_tc && P->lstm_tc && P->dec_wgrad_passes == 1 && nh == 1024 && Bd <= 256;
+  // Norm-only dW_pred (fused inner step: one bf16 pass, 0.39 ms at full width) on a side stream UNDER the two backward
+  // recurrences, on the 20 SMs their 128 persistent CTAs leave idle.  The backward recurrence runs clusters of 4: with
+  // 18-19 SMs per GPC exactly 4 clusters fit per GPC, so all 32 clusters fit only if the GEMM's CTAs sit on the LEFT-OVER
+  // SMs — round 1 started the GEMM first and the step got slower (10.22 vs 9.49 ms).  Now the side stream waits on a device
+  // flag that the recurrence sets once its whole grid is resident (k_wait_flag), and it is joined at the END of the backward
+  // pass (the encoder recurrence re-uses the same cluster placement).  Not used when the data-parallel hook wants the
+  // decoder gradients early.  LAGVAE_SIDE_WGRAD=0 turns it off; LAGVAE_SIDE_WGRAD_FRAC=f sends only the first f·V rows.
+  static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return !(e && e[0] == '0'); }();
+  static const float side_frac = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD_FRAC"); const float f = e ? (float)atof(e) : 1.f;
+                                      return f < 0.f ? 0.f : (f > 1.f ? 1.f : f); }();
+  const bool side_wgrad = side_env && side_frac > 0.f && P->use_tc && P->lstm_tc && P->dec_wgrad_passes == 1 && nh >= 256 &&
+                          Bd <= 64 && !P->dec_ev && V >= 1024;
   bool side_pending = false;
+  int side_rows = 0;
+  Staged side_sdl{}, side_sh{};
 
   LV_TRY(combine_upstream(g_loss, g_rec, g_kl, P->kl_weight, B, P->g_rec, P->g_kl, st));
 
@@ -769,16 +780,17 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
         LV_CUDA(cudaEventCreateWithFlags(&P->side_fork, cudaEventDisableTiming));
         LV_CUDA(cudaEventCreateWithFlags(&P->side_join, cudaEventDisableTiming));
       }
-      LV_CUDA(cudaEventRecord(P->side_fork, st));          // operands staged, dH GEMM enqueued ahead of the recurrence
-      LV_CUDA(cudaStreamWaitEvent(P->side, P->side_fork, 0));
-      gemm_tc_set_grid_cap(20);                            // 148 SMs - 128 recurrence CTAs
-      const int rs = mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
-                        P->dec_wgrad_passes, P->side);
-      gemm_tc_set_grid_cap(0);
-      LV_TRY(rs);
-      LV_CUDA(cudaEventRecord(P->side_join, P->side));
-      side_pending = true;
-      P->arena_floor = P->arena_off;                       // dlogits / H_drop staging stays live until the join
+      const int Vs = side_frac >= 1.f ? V : (int)((int64_t)(side_frac * V) / 128 * 128);   // rows [0, Vs) on the side stream
+      if (Vs < V)    // the rest at full width, here
+        LV_TRY(mm(P, sub(sdl, 0, rd, Vs, V - Vs), true, sh, true, gr->p[D_PRED] + (int64_t)Vs * nh, nh, V - Vs, nh, (int)rd,
+                  1.f, 0.f, nullptr, nullptr, 0, P->dec_wgrad_passes, st));
+      LV_CUDA(cudaMemsetAsync(P->side_gate, 0, sizeof(unsigned), st));
+      LV_CUDA(cudaEventRecord(P->side_fork, st));          // operands staged, gate cleared; the recurrence is launched next
+      side_rows = Vs;
+      side_sdl = sdl;
+      side_sh = sh;
+      side_pending = Vs > 0;
+      P->arena_floor = P->arena_off;                       // dlogits staging stays live until the join
     } else {
       LV_TRY(mm(P, sdl, true, sh, true, gr->p[D_PRED], nh, V, nh, (int)rd, 1.f, 0.f, nullptr, nullptr, 0,
                 P->dec_wgrad_passes, st));
@@ -795,10 +807,26 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   if (P->lstm_tc)
     LV_TRY(lstm_tc_backward(P->lstm_tc, w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc, P->dh_rec,
                             P->dgates_d, Td, Bd, true, st, P->dzb, const_cast<uint16_t*>(sdg_k.tc.hi),
-                            const_cast<uint16_t*>(sdg_k.tc.lo), &extras));
+                            const_cast<uint16_t*>(sdg_k.tc.lo), &extras, side_pending ? P->side_gate : nullptr));
   else
     LV_TRY(lstm_backward_steps(w->p[D_WHH], P->c0, P->gates_d, P->c_d, P->dh_d, dout, nullptr, P->dc,
                                P->dh_rec, P->dgates_d, Td, Bd, nh, true, st));
+  if (side_pending) {
+    // enqueued AFTER the recurrence launch: fork -> wait until the recurrence's grid is resident -> GEMM on the idle SMs
+    LV_CUDA(cudaStreamWaitEvent(P->side, P->side_fork, 0));
+    int rs = wait_flag(P->side_gate, 2000000LL, P->side);           // gives up after ~1 ms (v1 / SIMT recurrence never sets it)
+    if (rs == LAGVAE_OK) {
+      gemm_tc_set_grid_cap(20);                                     // 148 SMs - 128 recurrence CTAs
+      rs = mm(P, sub(side_sdl, 0, rd, 0, side_rows), true, side_sh, true, gr->p[D_PRED], nh, side_rows, nh, (int)rd, 1.f, 0.f,
+              nullptr, nullptr, 0, P->dec_wgrad_passes, P->side);
+      gemm_tc_set_grid_cap(0);
+    }
+    LV_CUDA(cudaEventRecord(P->side_join, P->side));
+    if (rs != LAGVAE_OK) {
+      cudaStreamWaitEvent(st, P->side_join, 0);
+      return rs;
+    }
+  }
   if (!extras) LV_TRY(time_sum(P->dgates_d, Td, Bd, 4 * nh, P->dzb, st));
   LV_TRY(col_sum(P->dzb, Bd, 4 * nh, gr->p[D_BIH], gr->p[D_BHH], st));
   {
@@ -834,11 +862,6 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
                   nullptr, 0, st));
   LV_TRY(gemm_f32(P->dc0t, nh, 1, w->p[D_TRANS], 1, nz, P->dz, nz, Bd, nz, nh, 1.f, 1.f, nullptr, nullptr, 0, st));
 
-  if (side_pending) {   // dW_pred finished long ago (≈1.1 ms on 20 SMs vs 1.7 ms of recurrence): join, free its staging
-    LV_CUDA(cudaStreamWaitEvent(st, P->side_join, 0));
-    side_pending = false;
-    P->arena_floor = P->fwd_arena_end;
-  }
   // all 7 decoder gradients are final here: data-parallel callers may start reducing them (lagvae.h)
   if (P->dec_ev) {
     LV_CUDA(cudaEventRecord(P->dec_ev, st));
@@ -854,7 +877,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
                   0, st));
 
   // ---- encoder LSTM backward
-  P->arena_off = P->fwd_arena_end;
+  P->arena_off = P->arena_floor;       // == fwd_arena_end unless the side stream still reads the dlogits staging
   Staged sdg_ke = P->lstm_tc && P->use_tc && !no_extras ? stage_alloc(P, re, 4 * nh, &status) : Staged{};
   LV_TRY(status);
   bool extras_e = false;
@@ -885,6 +908,10 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   }
   LV_TRY(fill(gr->p[E_EMB], 0.f, (int64_t)V * ni, st));
   LV_TRY(embed_scatter_add(x, d.T, 0, B, 1, Te, P->dx_e, ni, spec_none(), gr->p[E_EMB], -1, st));
+  if (side_pending) {   // dW_pred ran under the two recurrences: join before the gradients are handed back
+    LV_CUDA(cudaStreamWaitEvent(st, P->side_join, 0));
+    P->arena_floor = P->fwd_arena_end;
+  }
   return LAGVAE_OK;
 }
 
