@@ -105,7 +105,7 @@ def test_graphed_window_of_fused_inner_steps_equals_eager(shape):
     # fresh masks per step: two steps on different masks cannot produce the same reconstruction sum
     assert float(want_sc[0][1]) != float(want_sc[1][1])
     if nh >= 256 and B <= 32:
-        assert lagvae.lstm_variant("forward").startswith("v2")   # the cooperative cluster kernels were captured
+        assert lagvae.lstm_variant()["forward"].startswith("v2")   # the cooperative cluster kernels were captured
 
 
 class _Vocab(dict):
@@ -143,8 +143,6 @@ def test_graphed_module_loss_in_train_mode_draws_fresh_masks():
     def eager():
         for q in params:
             q.grad = None
-        torch.manual_seed(42)
-        torch.cuda.manual_seed(42)                      # same eps draw every time: only the masks differ between calls
         loss, rec, kl = vae.loss(x, 0.5, nsamples=1)
         loss.mean(dim=-1).backward()
         return loss.detach().clone(), [q.grad.detach().clone() for q in params]
@@ -162,7 +160,6 @@ def test_graphed_module_loss_in_train_mode_draws_fresh_masks():
 
     # eps inside a captured vae.loss comes from torch's graph-safe generator: compare on the reconstruction masks through a
     # fixed eps instead — patch the draw for this test only
-    import modules.vae as MV
     word = lagvae.graph.philox_word(dev)
     orig = torch.Tensor.normal_
     try:

@@ -1263,10 +1263,17 @@ static int v2_launch(const LstmTcState* s, const RecArgs& a, const TMaps& tm, si
   // co-resident (the per-step grid barrier needs that), -1 = they are not (the caller picks another cluster size).
   // After a positive decision a failing launch is an ERROR: nothing falls back silently (lagvae_lstm_variant reports
   // what ran).  The kernel spins on a grid-wide counter, so the launch is always cooperative.
+  // The decision depends on the shared-memory footprint (a small nh leaves room for two CTAs per SM, nh = 1024 does not):
+  // it is re-made whenever the footprint differs from the one it was made for.
   static int state[16] = {0};
+  static size_t state_smem[16] = {0};
   int dev = 0;
   LV_CUDA(cudaGetDevice(&dev));
   int& stt = state[dev & 15];
+  if (state_smem[dev & 15] != smem) {
+    state_smem[dev & 15] = smem;
+    stt = 0;
+  }
   *launched = false;
   if (stt < 0) return LAGVAE_OK;
   auto kern = k_lstm_v2<FWD, CS_>;
