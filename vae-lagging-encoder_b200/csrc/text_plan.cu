@@ -739,10 +739,17 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   // pass (the encoder recurrence re-uses the same cluster placement).  Not used when the data-parallel hook wants the
   // decoder gradients early.  LAGVAE_SIDE_WGRAD=0 turns it off; LAGVAE_SIDE_WGRAD_FRAC=f sends only the first f·V rows.
   static const bool side_env = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD"); return !(e && e[0] == '0'); }();
-  static const float side_frac = [] { const char* e = getenv("LAGVAE_SIDE_WGRAD_FRAC"); const float f = e ? (float)atof(e) : 1.f;
-                                      return f < 0.f ? 0.f : (f > 1.f ? 1.f : f); }();
-  const bool side_wgrad = side_env && side_frac > 0.f && P->use_tc && P->lstm_tc && P->dec_wgrad_passes == 1 && nh >= 256 &&
-                          Bd <= 64 && !P->dec_ev && V >= 1024;
+  // The full-precision (3-pass) dW_pred of the module path is 2.4x the work: only its first rows fit under the recurrences
+  // (LAGVAE_SIDE_WGRAD_FRAC3, default 0.35), the rest runs at full width as before.
+  auto frac_env = [](const char* name, float dflt) { const char* e = getenv(name); const float f = e ? (float)atof(e) : dflt;
+                                                     return f < 0.f ? 0.f : (f > 1.f ? 1.f : f); };
+  static const float side_frac1 = frac_env("LAGVAE_SIDE_WGRAD_FRAC", 1.f);
+  static const float side_frac3 = frac_env("LAGVAE_SIDE_WGRAD_FRAC3", 0.35f);
+  // calibrated at B*ns = 32, V = 20001 (the recurrences' duration does not grow with either, the GEMM's work does)
+  const float side_frac = (P->dec_wgrad_passes == 1 ? side_frac1 : side_frac3) * std::min(1.f, 32.f / (float)Bd) *
+                          std::min(1.f, 20480.f / (float)V);
+  const bool side_wgrad = side_env && side_frac > 0.f && P->use_tc && P->lstm_tc && nh >= 256 && Bd <= 64 && !P->dec_ev &&
+                          V >= 1024;
   bool side_pending = false;
   int side_rows = 0;
   Staged side_sdl{}, side_sh{};
@@ -780,7 +787,7 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
         LV_CUDA(cudaEventCreateWithFlags(&P->side_fork, cudaEventDisableTiming));
         LV_CUDA(cudaEventCreateWithFlags(&P->side_join, cudaEventDisableTiming));
       }
-      const int Vs = side_frac >= 1.f ? V : (int)((int64_t)(side_frac * V) / 128 * 128);   // rows [0, Vs) on the side stream
+      const int Vs = side_frac >= 1.f ? V : (int)((int64_t)(side_frac * (float)V) / 128 * 128);   // rows [0, Vs) on the side stream
       if (Vs < V)    // the rest at full width, here
         LV_TRY(mm(P, sub(sdl, 0, rd, Vs, V - Vs), true, sh, true, gr->p[D_PRED] + (int64_t)Vs * nh, nh, V - Vs, nh, (int)rd,
                   1.f, 0.f, nullptr, nullptr, 0, P->dec_wgrad_passes, st));
