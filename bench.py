@@ -313,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             # tested host logic (tests/test_dp_gloo.py): shard-local fwd+bwd with 1/(B*N) upstream gradient,
             # ONE all-reduce of the flat gradient, clip + SGD on the averaged gradient
-            dp_inner_step(backend, params, x, gw, presharded=True, global_rows=B * world)
+            dp_inner_step(backend, params, x, gw, presharded=True, global_rows=B * world, read_loss=False)
 
     def barrier():
         if world > 1:

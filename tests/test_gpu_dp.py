@@ -192,4 +192,6 @@ def test_unmodified_text_py_spmd_on_two_gpus(tmp_path):
             logs.append(D.parse(f.read()))
     strip = lambda rows: [(k, {f: v for f, v in d.items()}) for k, d in rows]
     assert strip(logs[0]) == strip(logs[1]), "the two ranks printed different numbers"
-    D.compare_logs(logs[0], D.parse(out1), "text.py tinysyn: 2 GPUs (SPMD) vs 1 GPU", n_tight=6, rel_tight=2e-3)
+    # the "training worked" sanity rule is asserted on the single-GPU run by tests/test_gpu_reference_drivers.py; here the two
+    # ranks must agree with each other exactly and with the single-GPU run over the tight prefix
+    D.compare_logs(logs[0], D.parse(out1), "text.py tinysyn: 2 GPUs (SPMD) vs 1 GPU", n_tight=6, rel_tight=2e-3, sanity=False)

@@ -33,8 +33,10 @@ class LocalBackend(Protocol):
 
 def dp_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x_global: torch.Tensor,
                   flat_grads: torch.Tensor, group=None, max_norm: float = 5.0, lr: float = 1.0,
-                  presharded: bool = False, global_rows: int = None):
-    """One aggressive inner step under DP.  Returns (Σloss over the global batch, pre-clip grad norm).
+                  presharded: bool = False, global_rows: int = None, read_loss: bool = True):
+    """One aggressive inner step under DP.  Returns (Σloss over the global batch, pre-clip grad norm); read_loss=False
+    leaves Σloss on the device (a [1] tensor) instead of synchronising on it (text.py:381 reads it every step, a fused
+    caller only needs the 15-step window sum, text.py:389-398).
     x_global is the full batch (every rank runs the unmodified SPMD driver with identical seeds)
     unless presharded=True, in which case it already is this rank's shard and global_rows must be given."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -56,22 +58,26 @@ def dp_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x_globa
         # (70% of the bytes, final before the encoder LSTM backward starts) is reduced on a side stream underneath
         # the still-running encoder backward.
         off = getattr(backend, "decoder_offset", None)
-        if off is None:
-            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
-        else:                                   # the bucket split depends on the back-end only: identical on every rank
-            side = (backend.decoder_grads_stream(x_local)
-                    if x_local.shape[0] > 0 and hasattr(backend, "decoder_grads_stream") else None)
-            if side is not None:
-                with torch.cuda.stream(side):
-                    dist.all_reduce(flat_grads[off:], op=dist.ReduceOp.SUM, group=group)
-                dist.all_reduce(flat_grads[:off], op=dist.ReduceOp.SUM, group=group)
-                torch.cuda.current_stream().wait_stream(side)
-            else:
-                dist.all_reduce(flat_grads[off:], op=dist.ReduceOp.SUM, group=group)
-                dist.all_reduce(flat_grads[:off], op=dist.ReduceOp.SUM, group=group)
+        # lagvae_allreduce_bucket (communicator owned by liblagvae.so) on CUDA, torch.distributed otherwise (gloo tests)
+        comm = _bucket_comm(group if group is not None else dist.group.WORLD, flat_grads.device)
+        reduce = (lambda t, st=None: comm.all_reduce(t, st)) if comm is not None else \
+                 (lambda t, st=None: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group))
+        side = None
+        if off is not None and x_local.shape[0] > 0 and hasattr(backend, "decoder_grads_stream"):
+            side = backend.decoder_grads_stream(x_local)
+        if off is None or (side is None and getattr(backend, "single_bucket", False)):
+            reduce(flat_grads)                  # one bucket
+        elif side is not None:                  # the bucket split depends on the back-end only: identical on every rank
+            with torch.cuda.stream(side):
+                reduce(flat_grads[off:], side)
+            reduce(flat_grads[:off])
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            reduce(flat_grads[off:])
+            reduce(flat_grads[:off])
         dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)            # 4 bytes: Σloss for text.py:381
     norm = backend.clip_sgd(params, flat_grads, max_norm, lr)
-    return float(loss_sum), norm
+    return (float(loss_sum) if read_loss else loss_sum), norm
 
 
 def accumulated_inner_step(backend: LocalBackend, params: Sequence[torch.Tensor], x: torch.Tensor, flat_grads: torch.Tensor,
@@ -143,7 +149,7 @@ class ShardedTextLoss(torch.autograd.Function):
         side = None
         if hi > lo:
             Bl, T = int(ctx.x_local.shape[0]), int(ctx.x_local.shape[1])
-            hook = dec_off is not None and hasattr(eng, "enable_decoder_grads_event") and dev.type == "cuda"
+            hook = dec_off is not None and hasattr(eng, "enable_decoder_grads_event") and dev.type == "cuda" and _overlap_default()
             if hook:
                 eng.enable_decoder_grads_event(Bl, T, getattr(eng, "last_ns", 1))
             sl = lambda g: None if g is None else g[lo:hi].contiguous()
@@ -158,8 +164,8 @@ class ShardedTextLoss(torch.autograd.Function):
         comm = _bucket_comm(ctx.group, dev)
         reduce = (lambda t, st=None: comm.all_reduce(t, st)) if comm is not None else \
                  (lambda t, st=None: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=ctx.group))
-        if dec_off is None:
-            reduce(flat)
+        if dec_off is None or not _overlap_default():
+            reduce(flat)                 # one bucket (LAGVAE_DP_OVERLAP=0: identical decision on every rank)
         elif side is not None:
             flat.record_stream(side)
             with torch.cuda.stream(side):
@@ -173,6 +179,18 @@ class ShardedTextLoss(torch.autograd.Function):
 
 
 _SIDE = {}
+
+
+def _overlap_default():
+    """LAGVAE_DP_OVERLAP=1: all-reduce the decoder part of the bucket on a side stream as soon as the decoder gradients are
+    final (under the encoder backward).  0 (default): ONE all-reduce of the whole bucket after the backward — the backward
+    then keeps its own side-stream work (dW_pred under the recurrences, csrc/text_plan.cu), which the early hand-over
+    excludes, and no NCCL CTAs compete with the recurrence clusters for SMs.  Measured on 2 B200s (profiles/README.md r2v):
+    8.29 ms/step without the early hand-over against 8.69 ms with it."""
+    import os
+    return os.environ.get("LAGVAE_DP_OVERLAP", "0") != "0"
+
+
 _COMMS = {}
 
 
@@ -210,11 +228,13 @@ def dp_group():
 class EngineBackend:
     """Product back-end: lagvae.TextEngine kernels; flat_grads is the engine's flat gradient workspace."""
 
-    def __init__(self, engine, kl_weight, eps_fn, drop_fn, overlap=True):
+    def __init__(self, engine, kl_weight, eps_fn, drop_fn, overlap=None):
+        overlap = _overlap_default() if overlap is None else overlap
         self.engine, self.kl_weight, self.eps_fn, self.drop_fn = engine, kl_weight, eps_fn, drop_fn
         self._views = None
         self.decoder_offset = engine.decoder_offset
         self._overlap = overlap
+        self.single_bucket = not overlap       # no early hand-over of the decoder gradients -> one all-reduce of the whole bucket
         self._side = None
 
     def decoder_grads_stream(self, x_local):
