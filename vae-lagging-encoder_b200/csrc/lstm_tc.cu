@@ -1443,7 +1443,7 @@ int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const f
       LV_TRY((v2_launch<false, 4>(s, a, tm, smem, st, &launched)));
       if (launched) { if (extras) *extras_done = true; return LAGVAE_OK; }
     }
-    cs_ok = 0;
+    // no cluster size fits THIS footprint: v1 for this call only (another shape may fit again; v2_launch caches its own decision)
     a.dgsum = nullptr; a.dg_hi = a.dg_lo = nullptr;
     a.KP = s->KPb; a.KB = s->KPb / 64;
     a.m_tiles = (int)cdiv(Bd, 64);
