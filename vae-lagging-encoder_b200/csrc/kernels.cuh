@@ -35,6 +35,8 @@ int ce_bwd_split(const float* logits, int64_t ld, int V, const int64_t* x, int64
                  const float* lse, const float* g_rec, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st);
 int ce_fused(const float* logits, int64_t ld, int V, const int64_t* x, int64_t x_ld, int Tn, int Bd, int ns, float g_row,
              float* lse_out, float* loss_row, uint16_t* hi, uint16_t* lo, int64_t ld_out, bool* done, cudaStream_t st);
+int embed_gather_split(const int64_t* x, int64_t x_ld, int t_off, int B, int ns, int Tn, const float* table, int ni,
+                       DropSpec drop, float* out, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st);
 int wait_flag(unsigned* flag, long long max_cycles, cudaStream_t st);
 int finalize_loss(const float* loss_row, const float* kl, int B, int ns, int Tn, float klw, float* loss,
                   float* rec, float* kl_out, float* scalars, cudaStream_t st);

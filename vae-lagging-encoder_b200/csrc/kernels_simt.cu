@@ -210,6 +210,48 @@ int embed_gather(const int64_t* x, int64_t x_ld, int t_off, int B, int ns, int T
   return LAGVAE_OK;
 }
 
+// Same gather, four columns per thread, emitting the fp32 rows AND the bf16 hi/lo tensor-core operand [rows, ld_out] of the
+// input projection in one pass (gather -> split -> GEMM were three passes over the tensor).  ni % 4 == 0,
+// ld_out % 4 == 0, ld_out >= ni (pad columns zero).  One Philox block serves the four elements.
+__global__ void __launch_bounds__(256)
+k_embed_gather_split(const int64_t* __restrict__ x, int64_t x_ld, int t_off, int B, int ns, int Tn,
+                     const float* __restrict__ table, int ni, DropSpec drop, float* __restrict__ out,
+                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out) {
+  const int Bd = B * ns;
+  const int q_row = ld_out >> 2;                          // float4 groups per output row (incl. padding)
+  const int64_t n = (int64_t)Tn * Bd * q_row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / q_row;
+    const int j = (int)(i - row * q_row) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j < ni) {
+      const int bd = (int)(row % Bd), t = (int)(row / Bd);
+      const int b = bd / ns;
+      const int64_t tok = x[(int64_t)b * x_ld + t_off + t];
+      const float4 e = *(const float4*)(table + tok * ni + j);
+      float f[4];
+      drop_factor4(drop, ((uint64_t)b * Tn + t) * ni + j, f);
+      v[0] = e.x * f[0]; v[1] = e.y * f[1]; v[2] = e.z * f[2]; v[3] = e.w * f[3];
+      *(float4*)(out + row * ni + j) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __nv_bfloat16 a[4], c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_bf16(v[k], a[k], c[k]);
+    *(uint2*)(hi + row * ld_out + j) = pack_bf16x4(a);
+    *(uint2*)(lo + row * ld_out + j) = pack_bf16x4(c);
+  }
+}
+int embed_gather_split(const int64_t* x, int64_t x_ld, int t_off, int B, int ns, int Tn, const float* table, int ni,
+                       DropSpec drop, float* out, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st) {
+  const int64_t n = (int64_t)Tn * B * ns * (ld_out / 4);
+  if (n <= 0) return LAGVAE_OK;
+  const int blocks = (int)std::min<int64_t>(cdiv(n, 256), 148 * 16);
+  k_embed_gather_split<<<blocks, 256, 0, st>>>(x, x_ld, t_off, B, ns, Tn, table, ni, drop, out, (__nv_bfloat16*)hi,
+                                               (__nv_bfloat16*)lo, (int)ld_out);
+  LV_LAUNCH_CHECK();
+  return LAGVAE_OK;
+}
+
 // dense embedding gradient: dTable[x[b,t], :] += dX[row, :] * keep  (autograd of nn.Embedding,
 // text.py:384; decoder row V-1 skipped: padding_idx=-1 -> V-1, dec_lstm.py:28)
 __global__ void k_embed_scatter_add(const int64_t* __restrict__ x, int64_t x_ld, int t_off, int B,

@@ -116,6 +116,15 @@ __host__ __device__ __forceinline__ bool philox_keep(uint64_t seed, uint32_t sid
   return u >= p;
 }
 
+// the four keep decisions of the aligned element group idx0 .. idx0+3 (idx0 % 4 == 0): ONE Philox block, same values as
+// philox_keep(idx0 + j)
+__host__ __device__ __forceinline__ void philox_keep4(uint64_t seed, uint32_t sid, uint64_t idx0, float p, bool keep[4]) {
+  uint32_t c[4] = {(uint32_t)(idx0 >> 2), (uint32_t)(idx0 >> 34), sid, 0x1a9fae5u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) keep[j] = (float)(c[j] >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
 struct DropSpec {  // resolved view of lagvae_dropout for one of the two masks
   int mode;        // 0 none, 1 mask, 2 philox
   float p, scale;  // scale = 1/(1-p)
@@ -129,6 +138,21 @@ __device__ __forceinline__ float drop_factor(const DropSpec& d, uint64_t idx) {
   if (d.mode == 1) return d.mask[idx] ? d.scale : 0.0f;
   const uint64_t key = d.seed_dev ? d.seed + __ldg((const unsigned long long*)d.seed_dev) : d.seed;
   return philox_keep(key, d.sid, idx, d.p) ? d.scale : 0.0f;
+}
+// same for an aligned group of four elements (idx0 % 4 == 0)
+__device__ __forceinline__ void drop_factor4(const DropSpec& d, uint64_t idx0, float f[4]) {
+  if (d.mode == 0) {
+    f[0] = f[1] = f[2] = f[3] = 1.0f;
+  } else if (d.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = d.mask[idx0 + j] ? d.scale : 0.0f;
+  } else {
+    const uint64_t key = d.seed_dev ? d.seed + __ldg((const unsigned long long*)d.seed_dev) : d.seed;
+    bool k[4];
+    philox_keep4(key, d.sid, idx0, d.p, k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = k[j] ? d.scale : 0.0f;
+  }
 }
 
 // ---- internal launchers shared between translation units --------------------------------------

@@ -220,6 +220,30 @@ Staged stage(lagvae_text_plan* P, Mat m, cudaStream_t st, int* status) {
   return s;
 }
 
+Staged stage_alloc(lagvae_text_plan* P, int64_t rows, int64_t cols, int* status);
+
+// embedding gather (+ input dropout) producing the fp32 rows and, on the tensor-core tier, the bf16 hi/lo operand in the SAME
+// pass (k_embed_gather_split); falls back to gather + stage when the table rows are not float4-aligned
+Staged gather_staged(lagvae_text_plan* P, const int64_t* x, int64_t x_ld, int B, int ns, int Tn, const float* table, int ni,
+                     DropSpec drop, float* out, int64_t rows, cudaStream_t st, int* status) {
+  static const bool off = [] { const char* e = getenv("LAGVAE_GATHER_SPLIT"); return e && e[0] == '0'; }();
+  if (P->use_tc && !off && (ni & 3) == 0 && ((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    Staged s = stage_alloc(P, rows, ni, status);
+    if (*status != LAGVAE_OK) return s;
+    s.m = Mat{out, rows, ni, ni};
+    const int r = embed_gather_split(x, x_ld, 0, B, ns, Tn, table, ni, drop, out, const_cast<uint16_t*>(s.tc.hi),
+                                     const_cast<uint16_t*>(s.tc.lo), s.tc.ld, st);
+    if (r != LAGVAE_OK) *status = r;
+    return s;
+  }
+  const int r = embed_gather(x, x_ld, 0, B, ns, Tn, table, ni, drop, out, st);
+  if (r != LAGVAE_OK) {
+    *status = r;
+    return Staged{Mat{out, rows, ni, ni}, TcOperand{nullptr, nullptr, 0, 0}};
+  }
+  return stage(P, Mat{out, rows, ni, ni}, st, status);
+}
+
 // decoder weight operands through the cross-call cache: which = 0 -> x-columns of W_ih ([4nh, ni], ld ni+nz), 1 -> W_pred [V, nh]
 Staged stage_dec_weight(lagvae_text_plan* P, int which, Mat m, cudaStream_t st, int* status) {
   if (!P->use_tc || P->dec_epoch == 0 || P->wc == nullptr) return stage(P, m, st, status);
@@ -380,9 +404,9 @@ int encoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   const lagvae_text_dims& d = P->d;
   const int nh = d.nh, ni = d.ni;
   int status = LAGVAE_OK;
-  LV_TRY(embed_gather(x, d.T, 0, d.B, 1, P->Te, w->p[E_EMB], ni, spec_none(), P->xe, st));   // enc_lstm.py:58
+  Staged sx = gather_staged(P, x, d.T, d.B, 1, P->Te, w->p[E_EMB], ni, spec_none(), P->xe, P->re, st, &status);   // enc_lstm.py:58
+  LV_TRY(status);
   LV_TRY(vec_add(w->p[E_BIH], w->p[E_BHH], P->bsum_e, 4 * nh, st));
-  Staged sx = stage(P, Mat{P->xe, P->re, ni, ni}, st, &status);
   P->st_xe = sx;                                  // kept for the backward pass (dW_ih = dGᵀ·X)
   const size_t keep = P->arena_off;
   Staged sw = stage(P, Mat{w->p[E_WIH], 4 * nh, ni, ni}, st, &status);
@@ -415,8 +439,8 @@ int decoder_xproj(lagvae_text_plan* P, const lagvae_text_params* w, const int64_
   const int nh = d.nh, ni = d.ni, nz = d.nz, B = d.B, ns = d.ns, Td = P->Td;
   int status = LAGVAE_OK;
   *ran_tc = false;
-  LV_TRY(embed_gather(x, x_ld, 0, B, ns, Td, w->p[D_EMB], ni, spec_in(dr), P->xd, st));       // :80-81 (+:87-91)
-  Staged sxd = stage(P, Mat{P->xd, P->rd, ni, ni}, st, &status);
+  Staged sxd = gather_staged(P, x, x_ld, B, ns, Td, w->p[D_EMB], ni, spec_in(dr), P->xd, P->rd, st, &status);   // :80-81 (+:87-91)
+  LV_TRY(status);
   P->st_xd = sxd;
   Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);  // x-columns of W_ih
   LV_TRY(status);
