@@ -86,8 +86,13 @@ def main():
                               "tensor_frac_issued_x3": 3 * tf / peaks["bf16_tflops_sustained"],
                               "compulsory_hbm_gb": Hb / 1e9, "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
                               "floor_ms": {"tensor_x3": t_tensor, "hbm": t_hbm},
-                              "bound": "latency (800 dependent recurrence steps)" if t_lat > max(t_tensor, t_hbm) else
-                                       ("tensor" if t_tensor > t_hbm else "hbm"),
+                              # B <= 64: inter-SM latency of the 800 dependent steps.  Above that the time grows LINEARLY with
+                              # B although the tensor floor is 2.4x lower: the recurrence issues M=64 MMAs per 64-row tile and
+                              # re-streams its operand per tile, so its per-step cost scales with the rows — an
+                              # issue/operand-stream bound of k_lstm_v2, not latency
+                              "bound": ("latency (800 dependent recurrence steps)" if B <= 64 else
+                                        "recurrence MMA issue + operand streaming per 64-row tile (scales with B)")
+                                       if t_lat > max(t_tensor, t_hbm) else ("tensor" if t_tensor > t_hbm else "hbm"),
                               "loss_sum": float(sc[0]), "micro_batches": int(-(-B // MAX_ROWS)), "peaks": src}), flush=True)
             del eng, params, gw, xs
             torch.cuda.empty_cache()
