@@ -135,3 +135,33 @@ def test_bench_work_model_matches_survey_figures():
     enc_fwd = 2 * 32 * (200 * 512 * 4096 + 200 * 1024 * 4096 + 1024 * 64)
     assert abs(enc_fwd - 80.53e9) < 1e8                                  # encoder forward 80.53 GFLOP
     assert bench.METRIC.startswith("aggressive inner-loop encoder steps/sec")
+
+
+def test_dropout_struct_matches_the_header_and_graph_seed_word_arithmetic():
+    """lagvae_dropout gained `seed_dev` (ABI 2): the ctypes mirror must have the C layout (4 + 2*4 + pad, two pointers, u64,
+    pointer = 48 bytes on LP64) and the header must declare the field; the graph-side seed word advances by PHILOX_STEP mod 2^64
+    exactly as the eager seed does (lagvae/graph.py, modules/text.py::dropout_spec)."""
+    import ctypes as C
+    import torch
+    from lagvae import _backend as be
+    from lagvae import graph as G
+    names = [f[0] for f in be.Dropout._fields_]
+    assert names == ["mode", "p_in", "p_out", "mask_in", "mask_out", "seed", "seed_dev"]
+    assert C.sizeof(be.Dropout) == 48 and be.Dropout.seed_dev.offset == 40 and be.Dropout.seed.offset == 32
+    hdr = open(os.path.join(ROOT, "include", "lagvae.h")).read()
+    assert "const uint64_t* seed_dev;" in hdr and "#define LAGVAE_ABI_VERSION 2" in hdr
+    word = torch.zeros(1, dtype=torch.int64)
+    for k in range(1, 6):
+        G.bump_philox_word(word)
+        assert int(word) & (2 ** 64 - 1) == (k * G.PHILOX_STEP) & (2 ** 64 - 1)
+    G.bump_philox_word(word, times=3)
+    assert int(word) & (2 ** 64 - 1) == (8 * G.PHILOX_STEP) & (2 ** 64 - 1)
+    assert G.capture_serial() is None                     # no GraphedStep capture in progress
+
+
+def test_dp_overlap_default_is_one_bucket_after_the_backward(monkeypatch):
+    from lagvae import dp
+    monkeypatch.delenv("LAGVAE_DP_OVERLAP", raising=False)
+    assert dp._overlap_default() is False
+    monkeypatch.setenv("LAGVAE_DP_OVERLAP", "1")
+    assert dp._overlap_default() is True
