@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <cstring>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -845,7 +846,9 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
   if (side_pending) {
     // enqueued AFTER the recurrence launch: fork -> wait until the recurrence's grid is resident -> GEMM on the idle SMs
     LV_CUDA(cudaStreamWaitEvent(P->side, P->side_fork, 0));
-    int rs = wait_flag(P->side_gate, 2000000LL, P->side);           // gives up after ~1 ms (v1 / SIMT recurrence never sets it)
+    // the gate only when the cluster kernel (the one that sets the flag) was the one launched; k_wait_flag gives up after ~1 ms
+    const bool gated = P->lstm_tc && strncmp(lstm_last_variant(1), "v2", 2) == 0;
+    int rs = gated ? wait_flag(P->side_gate, 2000000LL, P->side) : LAGVAE_OK;
     if (rs == LAGVAE_OK) {
       gemm_tc_set_grid_cap(20);                                     // 148 SMs - 128 recurrence CTAs
       rs = mm(P, sub(side_sdl, 0, rd, 0, side_rows), true, side_sh, true, gr->p[D_PRED], nh, side_rows, nh, (int)rd, 1.f, 0.f,
