@@ -16,6 +16,7 @@
 // Rows of the 64-row UMMA tile beyond the batch are zero (never written) — TMEM layout for M=64:
 // row i -> lane 32*(i/16) + i%16 (cute/atom/mma_traits_sm100.hpp, tmem_frg M_MMA == 64).
 #include "lstm_tc.cuh"
+#include "kernels.cuh"
 #include "sm100_ptx.cuh"
 
 #include <cstdio>
@@ -66,6 +67,8 @@ struct RecArgs {
   int grouped;                   // v2: NS and the stages per step are multiples of bulk_stages -> the group partition is the same in
                                  // every step and only the group LEADERS' barriers are used (one commit / wait per group)
   int prod_fence;                // 1: producer-side fence.proxy.async before the arrival (round-1 behaviour; LAGVAE_LSTM_PROD_FENCE=1)
+  const float* row_bias;         // forward, optional: [Bd, 4nh] added to the pre-activations of EVERY time step as they are loaded
+                                 // (the decoder's z contribution, dec_lstm.py:84,97) — saves a read-modify-write pass over gates
   unsigned* started;             // optional: set to 1 once every CTA of the persistent grid is running (a side stream gates work on it
                                  // so that it takes the SMs the clusters leave over and never the ones they need)
 };
@@ -717,6 +720,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lstm_v2(const RecArgs a) {
           const float4 x0 = *(const float4*)(g + q * nh);
           pin[q * 4 + 0] = x0.x; pin[q * 4 + 1] = x0.y; pin[q * 4 + 2] = x0.z; pin[q * 4 + 3] = x0.w;
         }
+        if (a.row_bias != nullptr) {
+          const float* rb = a.row_bias + (int64_t)b * 4 * nh + ub;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 z0 = __ldg((const float4*)(rb + q * nh));
+            pin[q * 4 + 0] += z0.x; pin[q * 4 + 1] += z0.y; pin[q * 4 + 2] += z0.z; pin[q * 4 + 3] += z0.w;
+          }
+        }
         const float* cpp = t ? a.c_all + ((int64_t)(t - 1) * Bd + b) * nh + ub : (a.c0 ? a.c0 + (int64_t)b * nh + ub : nullptr);
 #pragma unroll
         for (int j = 0; j < 4; ++j) pc[j] = cpp ? cpp[j] : 0.f;
@@ -1334,7 +1345,7 @@ static int make_maps(const LstmTcState* s, int Bd, int KP, int part_bytes, TMaps
 
 int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,
                     float* c_all, float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd,
-                    cudaStream_t st) {
+                    cudaStream_t st, const float* row_bias) {
   LV_CHECK_ARG(s && Bd <= s->max_bd && Tn > 0, "lstm_tc_forward: bad arguments");
   LV_TRY(configure(s));
   RecArgs a{};
@@ -1361,6 +1372,7 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
   a.dbg = (g_dbg && g_dbg_words >= (size_t)Tn * 8) ? g_dbg : nullptr;
   a.bar = s->bar; a.abuf = s->abuf; a.w_hh = w_hh; a.h0 = h0; a.c0 = c0; a.gates = gates; a.c_all = c_all;
   a.h_all = h_all; a.hdrop_all = hdrop_all; a.drop = drop;
+  a.row_bias = v2 ? row_bias : nullptr;          // the cluster kernel adds it as it loads the pre-activations
   LV_CUDA(cudaMemsetAsync(s->bar, 0, 256, st));
   // the K padding columns of the streamed buffer must be zero
   if (s->KPf != s->nh) LV_CUDA(cudaMemsetAsync(s->abuf, 0, (size_t)4 * Bd * s->KPf * 2, st));
@@ -1383,6 +1395,8 @@ int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const fl
     LV_CHECK_ARG(ring_geometry(s->wf, Bd, a.KB, &a.part_bytes, &a.NS, &smem), "lstm_tc_forward: no ring geometry");
     LV_TRY(make_maps(s, Bd, a.KP, a.part_bytes, &tm));
   }
+  a.row_bias = nullptr;                          // v1 does not know it: one streaming pass first
+  if (row_bias) LV_TRY(add_row_periodic(gates, row_bias, (int64_t)Tn * Bd, 4 * s->nh, Bd, st));
   void* args[] = {(void*)&a, (void*)&tm};
   LV_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_fwd_tc, dim3(s->G), dim3(NTHREADS), args, smem, st));
   lstm_note_variant(0, "v1");

@@ -16,7 +16,9 @@ void lstm_tc_set_debug(void* dev_u64, size_t words);   // optional clock64 trace
 // Same contracts as lstm_forward_steps / lstm_backward_steps in text_plan.cu.
 int lstm_tc_forward(LstmTcState* s, const float* w_hh, const float* h0, const float* c0, float* gates,
                     float* c_all, float* h_all, float* hdrop_all, DropSpec drop, int Tn, int Bd,
-                    cudaStream_t st);
+                    cudaStream_t st,
+                    // optional [Bd, 4nh]: added to the pre-activations of every time step (decoder z bias)
+                    const float* row_bias = nullptr);
 int lstm_tc_backward(LstmTcState* s, const float* w_hh, const float* c0, const float* gates,
                      const float* c_all, const float* dh_ext, DropSpec drop, const float* dh_last, float* dc,
                      float* dh_rec, float* dgates, int Tn, int Bd, bool want_init, cudaStream_t st,

@@ -477,9 +477,12 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   LV_TRY(gemm_f32(z, nz, 1, w->p[D_TRANS], nz, 1, P->c0, nh, Bd, nh, nz, 1.f, 0.f, nullptr, nullptr, 0,
                   st));                                                                      // :100
   LV_TRY(tanh_copy(P->c0, P->h0, Bd * nh, st));                                              // :101
+  const float* rec_bias = nullptr;
   if (xproj_state == 1) {
-    // tensor-core tier: plain GEMM (decoder_xproj), then the row-periodic z bias in one streaming pass (see k_add_row_periodic)
-    LV_TRY(add_row_periodic(P->gates_d, P->zb, P->rd, 4 * nh, Bd, st));
+    // tensor-core tier: plain GEMM (decoder_xproj); the row-periodic z bias is added by the persistent recurrence kernel as it
+    // loads the pre-activations (or in one streaming pass, k_add_row_periodic, on the tiers that cannot)
+    if (P->lstm_tc) rec_bias = P->zb;
+    else LV_TRY(add_row_periodic(P->gates_d, P->zb, P->rd, 4 * nh, Bd, st));
   } else {
     Staged swd = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
     LV_TRY(status);
@@ -488,7 +491,7 @@ int decoder_forward(lagvae_text_plan* P, const lagvae_text_params* w, const int6
   }
   float* hdrop = dout.mode ? P->hdrop_d : nullptr;
   if (P->lstm_tc)
-    LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st));
+    LV_TRY(lstm_tc_forward(P->lstm_tc, w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, st, rec_bias));
   else
     LV_TRY(lstm_forward_steps(w->p[D_WHH], P->h0, P->c0, P->gates_d, P->c_d, P->h_d, hdrop, dout, Td, Bd, nh,
                               st));                                                          // :104,106
