@@ -785,27 +785,30 @@ int wait_flag(unsigned* flag, long long max_cycles, cudaStream_t st) {
 
 // rec[b] = mean_s Σ_t loss_row ; loss[b] = rec + klw*KL   (dec_lstm.py:148, vae.py:95,98);
 // scalars[0..2] = Σloss, Σrec, ΣKL (text.py:381 reads Σloss).  Single block.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_finalize_loss(const float* __restrict__ loss_row, const float* __restrict__ kl, int B, int ns, int Tn,
                 float klw, float* __restrict__ loss, float* __restrict__ rec, float* __restrict__ kl_out,
                 float* __restrict__ scalars) {
   __shared__ float red[32];
   const int Bd = B * ns;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float sl = 0.f, sr = 0.f, sk = 0.f;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  // one warp per sentence: the lanes stride over (sample, time) — fixed summation order, Tn/32 dependent loads instead of Tn
+  for (int b = warp; b < B; b += nwarps) {
     float r = 0.f;
-    for (int s = 0; s < ns; ++s) {
-      float rs = 0.f;
-      for (int t = 0; t < Tn; ++t) rs += loss_row[(int64_t)t * Bd + b * ns + s];
-      r += rs;
+    for (int i = lane; i < ns * Tn; i += 32) {
+      const int s_ = i / Tn, t = i - s_ * Tn;
+      r += loss_row[(int64_t)t * Bd + b * ns + s_];
     }
-    r /= (float)ns;
-    const float k = kl[b];
-    const float l = r + klw * k;
-    loss[b] = l;
-    rec[b] = r;
-    if (kl_out && kl_out != kl) kl_out[b] = k;
-    sl += l; sr += r; sk += k;
+    r = warp_sum(r) / (float)ns;
+    if (lane == 0) {
+      const float k = kl[b];
+      const float l = r + klw * k;
+      loss[b] = l;
+      rec[b] = r;
+      if (kl_out && kl_out != kl) kl_out[b] = k;
+      sl += l; sr += r; sk += k;
+    }
   }
   sl = block_sum(sl, red);
   sr = block_sum(sr, red);
@@ -814,7 +817,7 @@ k_finalize_loss(const float* __restrict__ loss_row, const float* __restrict__ kl
 }
 int finalize_loss(const float* loss_row, const float* kl, int B, int ns, int Tn, float klw, float* loss,
                   float* rec, float* kl_out, float* scalars, cudaStream_t st) {
-  k_finalize_loss<<<1, 256, 0, st>>>(loss_row, kl, B, ns, Tn, klw, loss, rec, kl_out, scalars);
+  k_finalize_loss<<<1, 1024, 0, st>>>(loss_row, kl, B, ns, Tn, klw, loss, rec, kl_out, scalars);
   LV_LAUNCH_CHECK();
   return LAGVAE_OK;
 }

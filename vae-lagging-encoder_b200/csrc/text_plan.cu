@@ -871,8 +871,25 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     sdg.m = Mat{P->dgates_d, rd, 4 * nh, 4 * nh};
     if (!extras) sdg = stage(P, Mat{P->dgates_d, rd, 4 * nh, 4 * nh}, st, &status);
     Staged sxd = P->st_xd.tc.hi ? P->st_xd : stage(P, Mat{P->xd, rd, ni, ni}, st, &status);
-    // h_d itself (not its dropped-out version) pairs with dG in dW_hh: forward's copy serves only when dropout_out is off
-    Staged shd = (P->st_h.tc.hi && !dout.mode) ? P->st_h : stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
+    // h_d itself (not its dropped-out version) pairs with dG in dW_hh: forward's copy serves only when dropout_out is off.
+    // When it is staged here, h0 is staged in FRONT of it: [h0 ; h_0 .. h_{T-1}] makes dW_hh ONE GEMM over all T steps
+    // (rows t pair with row t of that operand) instead of a tensor GEMM over t >= 1 plus an fp32 GEMM for the h0 term.
+    Staged shd, shd_prev{};
+    if (P->st_h.tc.hi && !dout.mode) {
+      shd = P->st_h;
+    } else if (P->use_tc) {
+      Staged ext = stage_alloc(P, rd + Bd, nh, &status);
+      LV_TRY(status);
+      LV_TRY(split_bf16_launch(P->h0, nh, Bd, nh, const_cast<uint16_t*>(ext.tc.hi), const_cast<uint16_t*>(ext.tc.lo), ext.tc.ld, st));
+      LV_TRY(split_bf16_launch(P->h_d, nh, (int)rd, nh, const_cast<uint16_t*>(ext.tc.hi) + (int64_t)Bd * ext.tc.ld,
+                               const_cast<uint16_t*>(ext.tc.lo) + (int64_t)Bd * ext.tc.ld, ext.tc.ld, st));
+      shd_prev = ext;
+      shd_prev.m = Mat{nullptr, rd, nh, nh};
+      shd = sub(ext, Bd, rd, 0, nh);
+      shd.m = Mat{P->h_d, rd, nh, nh};
+    } else {
+      shd = stage(P, Mat{P->h_d, rd, nh, nh}, st, &status);
+    }
     Staged swx = stage_dec_weight(P, 0, Mat{w->p[D_WIH], 4 * nh, ni, ni + nz}, st, &status);
     LV_TRY(status);
     // dW_ih[:, :ni] = dGᵀ · X   ;  dW_ih[:, ni:] = dzbᵀ · z
@@ -881,11 +898,16 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
     LV_TRY(gemm_f32(P->dzb, 1, 4 * nh, P->z, 1, nz, gr->p[D_WIH] + ni, ni + nz, 4 * nh, nz, Bd, 1.f, 0.f, nullptr,
                     nullptr, 0, st));
     // dW_hh = Σ_t dG_tᵀ h_{t-1}: rows t>=1 pair with h_d[t-1]; t=0 pairs with h0
-    if (Td > 1)
-      LV_TRY(mm(P, sub(sdg, Bd, rd - Bd, 0, 4 * nh), true, sub(shd, 0, rd - Bd, 0, nh), true, gr->p[D_WHH], nh,
-                4 * nh, nh, (int)(rd - Bd), 1.f, 0.f, nullptr, nullptr, 0, P->dec_wgrad_passes, st));
-    LV_TRY(gemm_f32(P->dgates_d, 1, 4 * nh, P->h0, 1, nh, gr->p[D_WHH], nh, 4 * nh, nh, Bd, 1.f,
-                    Td > 1 ? 1.f : 0.f, nullptr, nullptr, 0, st));
+    if (shd_prev.tc.hi && sdg.tc.hi && rd >= 32 && nh >= 16) {
+      LV_TRY(mm(P, sdg, true, sub(shd_prev, 0, rd, 0, nh), true, gr->p[D_WHH], nh, 4 * nh, nh, (int)rd, 1.f, 0.f, nullptr,
+                nullptr, 0, P->dec_wgrad_passes, st));
+    } else {
+      if (Td > 1)
+        LV_TRY(mm(P, sub(sdg, Bd, rd - Bd, 0, 4 * nh), true, sub(shd, 0, rd - Bd, 0, nh), true, gr->p[D_WHH], nh,
+                  4 * nh, nh, (int)(rd - Bd), 1.f, 0.f, nullptr, nullptr, 0, P->dec_wgrad_passes, st));
+      LV_TRY(gemm_f32(P->dgates_d, 1, 4 * nh, P->h0, 1, nh, gr->p[D_WHH], nh, 4 * nh, nh, Bd, 1.f,
+                      Td > 1 ? 1.f : 0.f, nullptr, nullptr, 0, st));
+    }
     // dX = dG · W_ih[:, :ni]  -> dense decoder embedding gradient (row V-1 = padding_idx, no grad)
     LV_TRY(mm(P, sdg, false, swx, true, P->dx_d, ni, (int)rd, ni, 4 * nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
   }
