@@ -498,9 +498,10 @@ def run_ours(args, rank, world, local_rank):
             "step_tensor_frac": F / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peak)}
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3-split operands (hi*hi + hi*lo + lo*hi), f32 accumulate/state; in `value` the three decoder "
-                     "weight-gradient GEMMs (dW_pred, decoder dW_ih, dW_hh: never applied in the inner loop, they only enter "
-                     "the clip norm) run ONE bf16 pass; `e2e` runs all GEMMs 3-pass",
+            "dtype": "bf16x3-split operands (hi*hi + hi*lo + lo*hi), f32 accumulate/state; in `value` and `graph` the four decoder "
+                     "weight-gradient GEMMs (dW_pred, decoder dW_ih, dW_hh and the dX that feeds only the decoder embedding "
+                     "gradient: never applied in the inner loop, they only enter the clip norm) run ONE bf16 pass; `e2e` runs "
+                     "all GEMMs 3-pass",
             "data": "synthetic", "repeats_ms": rep_ms, "lstm_variant": variant,
             "config": {"workload": "configs[1]: Yahoo LSTM-VAE aggressive inner step (text.py:371-391), B=32/GPU T=200 V=20001 ni=512 nh=1024 nz=32, "
                                    "train-mode dropout 0.5/0.5, kl_weight 0.1, SGD lr 1.0, clip 5.0",

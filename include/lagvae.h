@@ -111,7 +111,7 @@ int lagvae_text_loss_forward(lagvae_text_plan* plan, const lagvae_text_params* p
  * gradients (overwritten, not accumulated); decoder.embed.weight row V-1 gets zeros
  * (padding_idx=-1, dec_lstm.py:28). */
 #define LAGVAE_BWD_DEFAULT 0u
-/* The decoder WEIGHT gradients (pred_linear, decoder lstm weight_ih/hh) feed only the clip norm in the aggressive
+/* The decoder WEIGHT gradients (pred_linear, decoder lstm weight_ih/hh, decoder embedding) feed only the clip norm in the aggressive
  * loop (text.py:385; the decoder is not stepped, text.py:387): compute them with ONE bf16 pass instead of three
  * (norm error ~1e-5).  Everything that reaches the encoder update stays fp32-grade. */
 #define LAGVAE_BWD_DECODER_WGRAD_NORM_ONLY 1u

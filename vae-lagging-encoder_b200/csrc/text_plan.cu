@@ -908,8 +908,10 @@ int lagvae_text_loss_backward(lagvae_text_plan* P, const lagvae_text_params* w, 
       LV_TRY(gemm_f32(P->dgates_d, 1, 4 * nh, P->h0, 1, nh, gr->p[D_WHH], nh, 4 * nh, nh, Bd, 1.f,
                       Td > 1 ? 1.f : 0.f, nullptr, nullptr, 0, st));
     }
-    // dX = dG · W_ih[:, :ni]  -> dense decoder embedding gradient (row V-1 = padding_idx, no grad)
-    LV_TRY(mm(P, sdg, false, swx, true, P->dx_d, ni, (int)rd, ni, 4 * nh, 1.f, 0.f, nullptr, nullptr, 0, 3, st));
+    // dX = dG · W_ih[:, :ni]  -> dense decoder embedding gradient (row V-1 = padding_idx, no grad).  It feeds ONLY the
+    // decoder embedding gradient — a decoder weight gradient like the three above: one bf16 pass when they are norm-only
+    LV_TRY(mm(P, sdg, false, swx, true, P->dx_d, ni, (int)rd, ni, 4 * nh, 1.f, 0.f, nullptr, nullptr, 0,
+              P->dec_wgrad_passes, st));
   }
   LV_TRY(fill(gr->p[D_EMB], 0.f, (int64_t)V * ni, st));
   LV_TRY(embed_scatter_add(x, d.T, 0, B, ns, Td, P->dx_d, ni, din, gr->p[D_EMB], V - 1, st));
