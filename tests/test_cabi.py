@@ -165,3 +165,11 @@ def test_dp_overlap_default_is_one_bucket_after_the_backward(monkeypatch):
     assert dp._overlap_default() is False
     monkeypatch.setenv("LAGVAE_DP_OVERLAP", "1")
     assert dp._overlap_default() is True
+
+
+def test_graft_entry_abi_check_agrees_with_header_binding_and_library():
+    """__graft_entry__.build() ends with this check (the driver runs build() on the CPU box every round)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as G
+    G.check_abi()
