@@ -68,19 +68,26 @@ def _worker(rank, world, port, B, out_q, two_buckets=False):
     flat = torch.zeros(sum(q.numel() for q in params))
     lo, hi = shard_bounds(B, rank, world)
     dec_off = sum(q.numel() for q in params[:6]) if two_buckets else None
-    loss_sum, norm = dp_inner_step(OracleBackend(eps, 0.5, lo, dec_off), params, x, flat, max_norm=0.05)
+    backend = OracleBackend(eps, 0.5, lo, dec_off)
+    if two_buckets == "single":       # the default of the product back-end: bucket split known, ONE all-reduce after the backward,
+        backend.single_bucket = True  # and Σloss left on the device (read_loss=False)
+        loss_sum, norm = dp_inner_step(backend, params, x, flat, max_norm=0.05, read_loss=False)
+        assert isinstance(loss_sum, torch.Tensor) and loss_sum.shape == (1,)
+        loss_sum = float(loss_sum)
+    else:
+        loss_sum, norm = dp_inner_step(backend, params, x, flat, max_norm=0.05)
     out_q.put((rank, loss_sum, norm, [q.numpy().copy() for q in params[:6]]))   # numpy: pickled by value (a torch tensor
     # travels as a shared-memory fd that dies with this process)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B,two_buckets", [(6, False), (5, False), (1, False), (5, True), (1, True)])
+@pytest.mark.parametrize("B,two_buckets", [(6, False), (5, False), (1, False), (5, True), (1, True), (5, "single"), (1, "single")])
 def test_two_rank_gloo_equals_single_process(B, two_buckets):
     """even, ragged, and an empty shard on rank 1; single bucket and the [decoder | encoder] split of the overlap path"""
     _setup_path()
     import lagging_oracle as O
-    world, port = 2, 29000 + os.getpid() % 2000 + B + (10 if two_buckets else 0)
+    world, port = 2, 29000 + os.getpid() % 2000 + B + (20 if two_buckets == "single" else (10 if two_buckets else 0))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, B, q, two_buckets)) for r in range(world)]
