@@ -173,3 +173,27 @@ def test_graft_entry_abi_check_agrees_with_header_binding_and_library():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as G
     G.check_abi()
+
+
+def test_public_method_surface_covers_the_reference_classes():
+    """Every public method of the reference's VAE / LSTMEncoder / LSTMDecoder / ResNetEncoderV2 / PixelCNNDecoderV2 exists
+    on the drop-in class of the same name (b1: 'same names'); needs the staged reference (scripts/stage_reference.sh)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_loader as RL
+    ref = RL.load_reference_modules()
+    if ref is None:
+        pytest.skip("reference not staged")
+    import modules as ours
+    missing = []
+    for cls in ("VAE", "LSTMEncoder", "LSTMDecoder", "ResNetEncoderV2", "PixelCNNDecoderV2"):
+        rc, oc = getattr(ref, cls, None), getattr(ours, cls, None)
+        if rc is None:
+            continue
+        assert oc is not None, cls
+        own = {n for n, v in vars(rc).items() if callable(v) and not n.startswith("_")}
+        for base in rc.__mro__[1:]:
+            if base.__module__.startswith("ref_modules"):
+                own |= {n for n, v in vars(base).items() if callable(v) and not n.startswith("_")}
+        missing += ["%s.%s" % (cls, n) for n in sorted(own) if not hasattr(oc, n)]
+    assert not missing, missing

@@ -133,6 +133,26 @@ class VAE(nn.Module):
     def sample_from_inference(self, x, nsamples=1):
         return self.encoder.sample(x, nsamples)[0]
 
+    def sample_from_posterior(self, x, nsamples):
+        """Metropolis-Hastings samples from the model posterior, [B, nsamples, nz] — vae.py:218-254.  The reference's version is
+        unreachable (it calls `encoder.sample_from_inference`, which no encoder defines, and no driver sets `args.mh_*`); this
+        is the same chain started from `self.sample_from_inference` so that the method exists with the documented contract.
+        Needs args.mh_burn_in / mh_thin / mh_std, like the reference."""
+        cur = self.sample_from_inference(x, 1)                       # [B, 1, nz]
+        cur_ll = self.eval_complete_ll(x, cur)                       # [B, 1]
+        total_iter = self.args.mh_burn_in + nsamples * self.args.mh_thin
+        samples = []
+        for it in range(total_iter):
+            nxt = torch.normal(mean=cur, std=cur.new_full(cur.size(), self.args.mh_std))
+            nxt_ll = self.eval_complete_ll(x, nxt)
+            accept = torch.min((nxt_ll - cur_ll).exp(), torch.ones_like(cur_ll))
+            mask = (torch.empty_like(accept).uniform_() < accept).float()
+            cur = mask.unsqueeze(2) * nxt + (1 - mask.unsqueeze(2)) * cur
+            cur_ll = mask * nxt_ll + (1 - mask) * cur_ll
+            if it >= self.args.mh_burn_in and (it - self.args.mh_burn_in) % self.args.mh_thin == 0:
+                samples.append(cur.unsqueeze(1))
+        return torch.cat(samples, dim=1)
+
     def calc_model_posterior_mean(self, x, grid_z):
         posterior = self.eval_log_model_posterior(x, grid_z).exp()
         return torch.mul(posterior.unsqueeze(2), grid_z.unsqueeze(0)).sum(1)
